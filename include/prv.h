@@ -1,0 +1,202 @@
+/*
+ * prv.h -- C ABI of libprv_b200.so: the B200 (sm_100a) implementation of NeRF-PRV's PRV_simulation
+ * ray-cast / coverage / greedy-selection / splat-render hot path.
+ *
+ * The reference (psc0628/NeRF-PRV) has no FFI/plugin layer: its boundary is the C++ class surface
+ * Share_Data / View / View_Space / Perception_3D (PRV_simulation/Share_Data.hpp, View_Space.hpp,
+ * main.cpp:17-286).  This header is what those classes bind instead of OctoMap / PCL-VTK; each entry
+ * point cites the reference code it replaces.  The host-side mirror of the classes lives in
+ * nerf-prv_b200/host/ and INTEGRATION.md shows the binding a maintainer adds to the reference.
+ *
+ * Conventions
+ *   - extern "C", POD only, caller owns every host buffer, ctx owns device memory / stream / events.
+ *   - every function returns PRV_OK (0) or a negative prv_status; nothing throws or aborts across the
+ *     ABI; prv_last_error(ctx) returns a static/ctx-owned message for the last failure.
+ *   - calls are synchronous at return unless named *_async; one ctx per GPU; a ctx is not re-entrant.
+ *   - there is NO CPU fallback: without a CUDA device prv_create fails with PRV_ERR_NO_DEVICE.
+ *   - matrices are row-major double[16]; "pose_world" is the reference's view_pose_world
+ *     (= now_camera_pose_world * view.pose.inverse(), main.cpp:72,109).
+ *   - "leaf order" is ColorOcTree::begin_leafs() order (ascending Morton code, z most significant in
+ *     each bit triple); it is the index i of cloud->points[i] (main.cpp:117-121) and the bit index of
+ *     the coverage bitsets.
+ */
+#ifndef PRV_B200_H
+#define PRV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRV_ABI_VERSION 1
+#define PRV_NONE 0xFFFFFFFFu /* "no voxel" in hit-rank tables */
+
+typedef enum prv_status {
+    PRV_OK = 0,
+    PRV_ERR_INVALID = -1,     /* bad argument / call order                       */
+    PRV_ERR_NO_DEVICE = -2,   /* no CUDA device / wrong architecture             */
+    PRV_ERR_CUDA = -3,        /* CUDA runtime error (see prv_last_error)         */
+    PRV_ERR_OOM = -4,         /* host or device allocation failed                */
+    PRV_ERR_UNSUPPORTED = -5, /* e.g. distortion models 3/5 (transcendental)     */
+    PRV_ERR_NCCL = -6,        /* NCCL not loadable / collective failed           */
+    PRV_ERR_IO = -7           /* file output failed                              */
+} prv_status;
+
+/* Same layout as rs2_intrinsics (Share_Data.hpp:79-89); model is the rs2_distortion enum (:67-76).
+ * coeffs are used BY INDEX exactly as rs2_project/deproject do (Share_Data.hpp:101-105,150-152). */
+typedef struct prv_intrinsics {
+    int   width;
+    int   height;
+    float ppx;
+    float ppy;
+    float fx;
+    float fy;
+    int   model;
+    float coeffs[5];
+} prv_intrinsics;
+
+/* Memory image of pcl::PointXYZRGB (32 bytes: xyz + 1.0f, bgra, 12 pad bytes) so prv_precept can
+ * write straight into cloud->points.data() (main.cpp:105,249,283). */
+typedef struct prv_point_xyzrgb {
+    float   x, y, z, w;
+    uint8_t b, g, r, a;
+    float   pad[3];
+} prv_point_xyzrgb;
+
+/* cast modes */
+#define PRV_MODE_VOXEL 0 /* precept-exact: one ray per occupied voxel through its truncated pixel (main.cpp:238-284) */
+#define PRV_MODE_DENSE 1 /* one ray per integer pixel (x,y) in [0,W)x[0,H)                                        */
+
+/* ray-march kernel variants (all must give identical results; tests enforce it) */
+#define PRV_VARIANT_PLAIN 0 /* literal sequential castRay march incl. max-range test every step           */
+#define PRV_VARIANT_FAST 1  /* + exact AABB pre-cull and exact early exit                                   */
+#define PRV_VARIANT_AXIS 2  /* + exact per-axis approach march (default)                                    */
+
+typedef struct prv_ctx prv_ctx;
+
+/* deterministic per-cast counters (oracle prints the same numbers; roofline numerators) */
+typedef struct prv_cast_stats {
+    uint64_t rays;       /* rays cast (dense: V*W*H; voxel: set pixels)            */
+    uint64_t probes_in;  /* DDA steps whose key lies inside the occupancy AABB     */
+    uint64_t hits;       /* rays with a first-hit voxel                            */
+    uint64_t steps;      /* DDA steps actually executed by the chosen variant      */
+} prv_cast_stats;
+
+/* per-kernel-class device time accumulated with CUDA events on the ctx stream since prv_timing_reset */
+typedef struct prv_timing {
+    float    cast_ms;     uint32_t cast_launches;
+    float    project_ms;  uint32_t project_launches;
+    float    count_ms;    uint32_t count_launches;
+    float    greedy_ms;   uint32_t greedy_launches;
+    float    splat_ms;    uint32_t splat_launches;
+    float    resolve_ms;  uint32_t resolve_launches;
+    float    other_ms;    uint32_t other_launches;
+} prv_timing;
+
+/* ---------------------------------------------------------------- lifecycle */
+int         prv_abi_version(void);
+int         prv_create(prv_ctx** ctx, int device);
+void        prv_destroy(prv_ctx* ctx);
+const char* prv_last_error(const prv_ctx* ctx); /* ctx may be NULL: last create error */
+int         prv_device_info(prv_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, uint64_t* mem_bytes);
+int         prv_sync(prv_ctx* ctx);
+int         prv_set_variant(prv_ctx* ctx, int variant);
+
+/* ---------------------------------------------------------------- host-side logic (pure host, no device)
+ * One implementation of the reference's pose / view-space / map-insertion arithmetic for every caller. */
+/* Eigen::Matrix4d::inverse() as used at main.cpp:72,109,244 and View_Space.hpp:73-137 */
+int prv_host_mat4_inverse(const double m[16], double out[16]);
+/* View::get_next_camera_pos(now_camera_pose_world, object_center_world, 0): View_Space.hpp:67-140 */
+int prv_host_view_pose(const double now_camera_pose_world[16], const double init_pos[3],
+                       const double object_center_world[3], double pose_out[16]);
+/* view_pose_world = now_camera_pose_world * pose.inverse(): main.cpp:72,109 */
+int prv_host_view_pose_world(const double now_camera_pose_world[16], const double pose[16], double out[16]);
+/* View_Space::get_view_space: View_Space.hpp:517-558.  init_pos_out has room for N rows; *n_views_out <= N. */
+int prv_host_view_space(const float* pts_xyz, uint64_t P, const double* pt_sphere, int N, double pt_norm,
+                        double view_space_radius, double center_out[3], double* predicted_size_out,
+                        double* init_pos_out, int* n_views_out);
+/* cloud normalisation of the NBV_Net_Labeler ctor: main.cpp:674 (toward pose 4), :768-790, :800-832, :1008-1010 */
+int prv_host_normalize_cloud(float* pts_xyz, uint64_t P, double target_size, double* predicted_size_before_out);
+/* ground_truth_model insertion loop + leaf enumeration: main.cpp:1005-1036, 1055-1058, 116-121.
+ * keys_out/rgb_out need room for P entries; *n_out = full_voxels. */
+int prv_host_build_map(const float* pts_xyz, const uint8_t* rgb, uint64_t P, double resolution,
+                       uint16_t* keys_out, uint8_t* rgb_out, uint32_t* n_out);
+
+/* ---------------------------------------------------------------- device inputs */
+/* ground_truth_model (Share_Data.hpp:258,458): occupied leaf keys in leaf order + voxel colours (may be NULL). */
+int prv_set_map(prv_ctx* ctx, const uint16_t* keys /* N x 3 */, const uint8_t* rgb /* N x 3 */, uint32_t N,
+                double resolution);
+/* share_data->color_intrinsics (Share_Data.hpp:388-399) and castRay's maxRange (main.cpp:258: 1.0) */
+int prv_set_camera(prv_ctx* ctx, const prv_intrinsics* intr, double max_range);
+/* candidate views: view_pose_world (main.cpp:109) and View::init_pos (snapped to a voxel centre on upload, main.cpp:112-114) */
+int prv_set_views(prv_ctx* ctx, const double* pose_world /* V x 16 */, const double* init_pos /* V x 3 */, uint32_t V);
+/* multi-GPU view sharding: global id of each local view (ties in the greedy argmax break on this id). NULL = 0..V-1 */
+int prv_set_view_ids(prv_ctx* ctx, const uint32_t* ids, uint32_t V);
+
+uint32_t prv_full_voxels(const prv_ctx* ctx);  /* share_data->full_voxels (main.cpp:1055-1058) */
+uint32_t prv_bitset_words(const prv_ctx* ctx); /* u64 words per coverage row (padded to 16 B)   */
+uint32_t prv_num_views(const prv_ctx* ctx);
+
+/* ---------------------------------------------------------------- resident path (inputs already in HBM)
+ * Kernels are enqueued on the ctx stream and the call returns without synchronising. */
+int prv_cast_async(prv_ctx* ctx, int mode, int want_pixels /* also write per-pixel hit rank + depth */);
+int prv_greedy_async(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter);
+
+/* ---------------------------------------------------------------- results (synchronise, then copy D2H) */
+int prv_get_bitsets(prv_ctx* ctx, uint64_t* out /* V x words */);
+int prv_get_coverage_counts(prv_ctx* ctx, uint32_t* out /* V */);
+/* dense: [V][H][W]; voxel mode: per-voxel [V][full_voxels] (rank seen by voxel i's ray) */
+int prv_get_hit_rank(prv_ctx* ctx, uint32_t view_begin, uint32_t view_count, uint32_t* out);
+int prv_get_depth(prv_ctx* ctx, uint32_t view_begin, uint32_t view_count, float* out); /* dense only */
+int prv_get_greedy(prv_ctx* ctx, uint32_t* seq, uint32_t* gains, uint32_t* n_out, uint64_t* covered_out /* words, may be NULL */);
+int prv_get_cast_stats(prv_ctx* ctx, prv_cast_stats* out);
+
+/* ---------------------------------------------------------------- host-buffer one-call API (what the classes bind) */
+/* Replaces the per-view loop over Perception_3D::precept (main.cpp:98-236, callers :1453,:1523,:1607).
+ * Any output pointer may be NULL.  Leaves the bitsets resident for prv_greedy. */
+int prv_cast_views(prv_ctx* ctx, const double* pose_world, const double* init_pos, uint32_t V, int mode,
+                   uint64_t* bitsets_out, uint32_t* coverage_count_out, uint32_t* hit_rank_out, float* depth_out);
+/* Perception_3D::precept for one view: fills cloud->points[0..full_voxels) (main.cpp:105,238-284).
+ * Returns PRV_OK; *view_in_map_out = 0 reproduces "View out of map.check." (main.cpp:139). */
+int prv_precept(prv_ctx* ctx, const double pose_world[16], const double init_pos[3], prv_point_xyzrgb* points_out,
+                int* view_in_map_out);
+/* greedy set-cover over the resident bitsets (frozen definition; tie rule of main.cpp:2006,2088,2152).
+ * seq/gains need max_iter+1 entries. */
+int prv_greedy(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter, uint32_t* seq, uint32_t* gains, uint32_t* n_out);
+
+/* ---------------------------------------------------------------- splat z-buffer render (replaces Perception_3D::render, main.cpp:68-96) */
+/* share_data->cloud_ground_truth (main.cpp:38) */
+int prv_set_cloud(prv_ctx* ctx, const float* xyz /* P x 3 */, const uint8_t* rgb /* P x 3 */, uint64_t P);
+/* Renders V views; rgba_out [V][H][W][4] already has white->alpha0 (Share_Data.hpp:771-784) and the
+ * 180-degree flip (main.cpp:1616) applied, i.e. it is the pixel content of rgbaClip_<i>.png.  depth_out [V][H][W] may be NULL. */
+int prv_render_views(prv_ctx* ctx, const double* pose_world, uint32_t V, int point_size, uint8_t* rgba_out,
+                     float* depth_out);
+int prv_render_async(prv_ctx* ctx, uint32_t V, int point_size); /* resident: uses prv_set_views poses, output stays on device */
+float prv_splat_focal(const prv_intrinsics* intr);
+
+/* ---------------------------------------------------------------- timing (CUDA events on the ctx stream) */
+int prv_timing_reset(prv_ctx* ctx);
+int prv_get_timing(prv_ctx* ctx, prv_timing* out); /* synchronises */
+int prv_event_record(prv_ctx* ctx, int slot /* 0..15 */);
+int prv_event_elapsed_ms(prv_ctx* ctx, int slot_begin, int slot_end, float* ms_out); /* synchronises on slot_end */
+/* counters since prv_reset_counters: kernels of this library launched, bytes copied host->device / device->host */
+int prv_reset_counters(prv_ctx* ctx);
+int prv_get_counters(prv_ctx* ctx, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* size of the dense occupancy bitmap in HBM (B_occ of the roofline formula) */
+int prv_map_bytes(prv_ctx* ctx, uint64_t* bitmap_bytes);
+/* writes >L2-size scratch so the next kernel starts cold */
+int prv_flush_l2(prv_ctx* ctx);
+
+/* ---------------------------------------------------------------- multi-GPU (one process per GPU; NCCL over NVLink) */
+int prv_comm_unique_id(void* id_out_128 /* ncclUniqueId bytes */);
+int prv_comm_init(prv_ctx* ctx, const void* id_128, int rank, int nranks);
+/* all-gathers the local coverage rows (equal V on every rank, view ids from prv_set_view_ids) so every rank
+ * holds the full table; the greedy then runs replicated and deterministic on every rank. */
+int prv_allgather_bitsets_async(prv_ctx* ctx);
+int prv_comm_destroy(prv_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRV_B200_H */

@@ -1,0 +1,1308 @@
+// prv_device.cu -- device side of include/prv.h: context, HBM layout, kernel launches, NCCL glue.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -Xcompiler -ffp-contract=off (see build.py).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/prv.h"
+#include "../host/prv_linalg.hpp"
+#include "prv_kernels.cuh"
+
+using namespace prvk;
+
+// =====================================================================================================
+// kernels
+// =====================================================================================================
+
+// One thread per pixel of a 32x8 tile (each warp an 8x4 patch, so the lanes of a warp march similar
+// step counts).  blockIdx.x = tile, blockIdx.y = view.
+template <int VARIANT, bool MASKED>
+__global__ void __launch_bounds__(256) raycast_kernel(const CastParams p) {
+    __shared__ ViewConst s_vc;
+    const uint32_t view = blockIdx.y + p.view_base;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.views + view);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_vc);
+        for (int i = threadIdx.x; i < (int)(sizeof(ViewConst) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const ViewConst& vc = s_vc;
+
+    const int tiles_x = (p.GW + 31) >> 5;
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = (tile_x << 5) + ((warp & 3) << 3) + (lane & 7);
+    const int py = (tile_y << 3) + ((warp >> 2) << 2) + (lane >> 3);
+    const bool in_grid = px < p.GW && py < p.GH;
+    const unsigned long long pid = (unsigned long long)py * p.GW + px;
+
+    bool active = in_grid && (vc.flags & kViewInMap) && !(vc.flags & kViewInObject);
+    if (MASKED && active) {
+        const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
+        active = (w >> (pid & 31)) & 1u;
+    }
+
+    CastResult res;
+    res.rank = kNone;
+    res.steps = 0;
+    res.probes = 0;
+    res.k0 = res.k1 = res.k2 = 0;
+    if (active) {
+        RayState r;
+        if (setup_ray(p.cam, vc, p.map.resolution, px, py, r)) {
+            if (VARIANT == PRV_VARIANT_PLAIN || !(vc.flags & kViewFastOk))
+                march_plain(p.map, p.cam, vc, r, res);
+            else if (VARIANT == PRV_VARIANT_FAST)
+                march_fast(p.map, vc, r, res);
+            else
+                march_axis(p.map, vc, r, res);
+        }
+    }
+
+    if (res.rank != kNone) {
+        uint32_t* row = p.bitsets32 + (size_t)view * (2u * p.map.words64);
+        const uint32_t bit = 1u << (res.rank & 31);
+        uint32_t* w = row + (res.rank >> 5);
+        if (!(*reinterpret_cast<volatile uint32_t*>(w) & bit)) atomicOr(w, bit);
+    }
+    if (in_grid && p.pix_hit && (!MASKED || active)) {
+        p.pix_hit[(size_t)view * p.pix_stride + pid] = res.rank;
+        if (p.pix_depth) {
+            float d = 0.0f;
+            if (res.rank != kNone) d = (float)__dsqrt_rn(dist_sq_at(vc, p.map.resolution, res.k0, res.k1, res.k2));
+            p.pix_depth[(size_t)view * p.pix_stride + pid] = d;
+        }
+    }
+
+    // deterministic counters: warp-reduce then one atomic per warp
+    unsigned long long c_rays = active ? 1ull : 0ull, c_probes = res.probes, c_hits = res.rank != kNone ? 1ull : 0ull, c_steps = res.steps;
+    for (int o = 16; o > 0; o >>= 1) {
+        c_rays += __shfl_down_sync(0xFFFFFFFFu, c_rays, o);
+        c_probes += __shfl_down_sync(0xFFFFFFFFu, c_probes, o);
+        c_hits += __shfl_down_sync(0xFFFFFFFFu, c_hits, o);
+        c_steps += __shfl_down_sync(0xFFFFFFFFu, c_steps, o);
+    }
+    if (lane == 0 && c_rays) {
+        atomicAdd(p.stats + 0, c_rays);
+        atomicAdd(p.stats + 1, c_probes);
+        atomicAdd(p.stats + 2, c_hits);
+        atomicAdd(p.stats + 3, c_steps);
+    }
+}
+
+// voxel-driven mode, stage 1 (main.cpp:243-251 of the reference): project every occupied voxel centre, mark its
+// TRUNCATED pixel in the (W+1)x(H+1) mask (pixel == W or == H passes the reference's '>' test).
+__global__ void __launch_bounds__(256) project_voxels_kernel(DevMap map, DevCam cam, const ViewConst* views, uint32_t view_base,
+                                                             uint32_t* mask, uint32_t mask_words, uint32_t* voxel_pix) {
+    const uint32_t view = blockIdx.y + view_base;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= map.n_occ) return;
+    const ViewConst& vc = views[view];
+    uint32_t pid = kNone;
+    if ((vc.flags & kViewInMap) && !(vc.flags & kViewInObject)) {
+        const float ex = (float)key_to_coord_d(map.keys[3 * i + 0], map.resolution);
+        const float ey = (float)key_to_coord_d(map.keys[3 * i + 1], map.resolution);
+        const float ez = (float)key_to_coord_d(map.keys[3 * i + 2], map.resolution);
+        const float vx = (float)row_apply(vc.inv + 0, (double)ex, (double)ey, (double)ez);
+        const float vy = (float)row_apply(vc.inv + 4, (double)ex, (double)ey, (double)ez);
+        const float vz = (float)row_apply(vc.inv + 8, (double)ex, (double)ey, (double)ez);
+        float u, v;
+        project_point_to_pixel(cam, vx, vy, vz, u, v);
+        // reject: pixel<0 || pixel>W (resp. H); NaN is rejected too (float->int of NaN is UB in the reference)
+        if (u >= 0.0f && u <= (float)cam.W && v >= 0.0f && v <= (float)cam.H) {
+            const int ix = (int)u, iy = (int)v;  // truncation at the int-parameter call, main.cpp:253
+            pid = (uint32_t)iy * (uint32_t)(cam.W + 1) + (uint32_t)ix;
+            atomicOr(mask + (size_t)view * mask_words + (pid >> 5), 1u << (pid & 31));
+        }
+    }
+    voxel_pix[(size_t)view * map.n_occ + i] = pid;
+}
+
+// voxel-driven mode, stage 3: voxel i takes the result of its pixel's ray
+__global__ void __launch_bounds__(256) gather_voxel_hits_kernel(uint32_t n_occ, const uint32_t* voxel_pix, const uint32_t* pix_hit,
+                                                                unsigned long long pix_stride, uint32_t* out) {
+    const uint32_t view = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_occ) return;
+    const uint32_t pid = voxel_pix[(size_t)view * n_occ + i];
+    out[(size_t)view * n_occ + i] = pid == kNone ? kNone : pix_hit[(size_t)view * pix_stride + pid];
+}
+
+// cloud->points image of Perception_3D::precept for one view (main.cpp:240-283)
+__global__ void __launch_bounds__(256) precept_points_kernel(DevMap map, const uint32_t* voxel_hit, prv_point_xyzrgb* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= map.n_occ) return;
+    prv_point_xyzrgb pt;
+    pt.x = pt.y = pt.z = 0.0f;
+    pt.w = 1.0f;
+    pt.b = pt.g = pt.r = 0;
+    pt.a = 255;
+    pt.pad[0] = pt.pad[1] = pt.pad[2] = 0.0f;
+    const uint32_t h = voxel_hit[i];
+    if (h != kNone) {
+        pt.x = (float)key_to_coord_d(map.keys[3 * h + 0], map.resolution);
+        pt.y = (float)key_to_coord_d(map.keys[3 * h + 1], map.resolution);
+        pt.z = (float)key_to_coord_d(map.keys[3 * h + 2], map.resolution);
+        pt.r = map.rgb[3 * h + 0];
+        pt.g = map.rgb[3 * h + 1];
+        pt.b = map.rgb[3 * h + 2];
+    }
+    out[i] = pt;
+}
+
+__device__ __forceinline__ uint32_t block_reduce_sum(uint32_t v, uint32_t* s_red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    uint32_t t = 0;
+    if (threadIdx.x < 32) {
+        t = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0u;
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xFFFFFFFFu, t, o);
+    }
+    return t;  // valid in thread 0
+}
+
+// coverage_count[v] = popcount(vis[v])
+__global__ void __launch_bounds__(256) popcount_rows_kernel(const uint64_t* rows, uint32_t words64, uint32_t* counts) {
+    __shared__ uint32_t s_red[8];
+    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(rows + (size_t)blockIdx.x * words64);
+    uint32_t c = 0;
+    for (uint32_t w = threadIdx.x; w < words64 / 2; w += blockDim.x) {
+        const ulonglong2 v = row[w];
+        c += __popcll(v.x) + __popcll(v.y);
+    }
+    const uint32_t t = block_reduce_sum(c, s_red);
+    if (threadIdx.x == 0) counts[blockIdx.x] = t;
+}
+
+// greedy set cover ---------------------------------------------------------------------------------
+// best[k] = max over views of (gain << 32) | (0xFFFFFFFF - view_id): largest gain, then LOWEST view id.
+__global__ void __launch_bounds__(256) greedy_init_kernel(const uint64_t* rows, uint32_t words64, uint32_t first_row, uint32_t first_id,
+                                                          unsigned long long* best) {
+    __shared__ uint32_t s_red[8];
+    const uint64_t* row = rows + (size_t)first_row * words64;
+    uint32_t c = 0;
+    for (uint32_t w = threadIdx.x; w < words64; w += blockDim.x) c += __popcll(row[w]);
+    const uint32_t t = block_reduce_sum(c, s_red);
+    if (threadIdx.x == 0) best[0] = ((unsigned long long)t << 32) | (unsigned long long)(0xFFFFFFFFu - first_id);
+}
+
+// iteration k >= 1: covered_k = covered_{k-1} | row[best_{k-1}];  score every view against covered_k.
+// Block 0 also materialises covered_k for the next launch.  score_only_cover: last launch, no scoring.
+__global__ void __launch_bounds__(256) greedy_iter_kernel(const uint64_t* rows, uint32_t words64, const uint32_t* view_ids,
+                                                          const uint32_t* row_of_id, uint32_t k, unsigned long long* best,
+                                                          const uint64_t* cov_prev, uint64_t* cov_next, int cover_only) {
+    __shared__ uint32_t s_red[8];
+    const unsigned long long prev = best[k - 1];
+    if (k > 1 && (prev >> 32) == 0ull) return;  // previous argmax had zero gain: selection is over
+    const uint32_t prev_id = 0xFFFFFFFFu - (uint32_t)(prev & 0xFFFFFFFFull);
+    const ulonglong2* rb = reinterpret_cast<const ulonglong2*>(rows + (size_t)row_of_id[prev_id] * words64);
+    const ulonglong2* cp = reinterpret_cast<const ulonglong2*>(cov_prev);
+    const ulonglong2* rv = reinterpret_cast<const ulonglong2*>(rows + (size_t)blockIdx.x * words64);
+    ulonglong2* cn = reinterpret_cast<ulonglong2*>(cov_next);
+    uint32_t c = 0;
+    for (uint32_t w = threadIdx.x; w < words64 / 2; w += blockDim.x) {
+        ulonglong2 cov = rb[w];
+        if (k > 1) {
+            const ulonglong2 o = cp[w];
+            cov.x |= o.x;
+            cov.y |= o.y;
+        }
+        if (blockIdx.x == 0) cn[w] = cov;
+        if (!cover_only) {
+            const ulonglong2 v = rv[w];
+            c += __popcll(v.x & ~cov.x) + __popcll(v.y & ~cov.y);
+        }
+    }
+    if (cover_only) return;
+    const uint32_t t = block_reduce_sum(c, s_red);
+    if (threadIdx.x == 0) atomicMax(best + k, ((unsigned long long)t << 32) | (unsigned long long)(0xFFFFFFFFu - view_ids[blockIdx.x]));
+}
+
+// splat z-buffer -------------------------------------------------------------------------------------
+// Stage 1: one 64-bit atomicMin per point on the CORNER cell of its footprint; stage 2 takes the min over the
+// point_size x point_size corner cells that cover a pixel.  min is associative, so this equals point_size^2 atomics
+// per point on the pixels themselves.
+__global__ void __launch_bounds__(256) splat_points_kernel(const float* xyz, uint64_t P, DevCam cam, const ViewConst* views,
+                                                           uint32_t view_base, float focal, int point_size, unsigned long long* corner,
+                                                           int Wc, int Hc) {
+    const uint32_t view_local = blockIdx.y;
+    const ViewConst& vc = views[view_local + view_base];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const double x = (double)xyz[3 * i + 0], y = (double)xyz[3 * i + 1], z = (double)xyz[3 * i + 2];
+    const float xc = (float)row_apply(vc.inv + 0, x, y, z);
+    const float yc = (float)row_apply(vc.inv + 4, x, y, z);
+    const float zc = (float)row_apply(vc.inv + 8, x, y, z);
+    if (!(zc > 0.01f && zc < 1000.01f)) return;
+    const float u = fadd(fmul(fdiv(xc, zc), focal), fmul((float)cam.W, 0.5f));
+    const float v = fadd(fmul(fdiv(yc, zc), focal), fmul((float)cam.H, 0.5f));
+    if (!(u > -64.0f && u < (float)cam.W + 64.0f && v > -64.0f && v < (float)cam.H + 64.0f)) return;
+    const float off = fsub(0.5f, fmul(0.5f, (float)point_size));
+    const int lx = (int)floorf(fadd(u, off)), ly = (int)floorf(fadd(v, off));
+    const int cx = lx + point_size - 1, cy = ly + point_size - 1;
+    if (cx < 0 || cx >= Wc || cy < 0 || cy >= Hc) return;
+    const unsigned long long packed = ((unsigned long long)__float_as_uint(zc) << 32) | (unsigned long long)(uint32_t)i;
+    atomicMin(corner + ((size_t)view_local * Hc + cy) * Wc + cx, packed);
+}
+
+__global__ void __launch_bounds__(256) splat_resolve_kernel(const unsigned long long* corner, int Wc, int Hc, int W, int H, int point_size,
+                                                            const uint8_t* rgb, uint8_t* rgba, float* depth, uint32_t view_base) {
+    extern __shared__ unsigned long long s_tile[];
+    const uint32_t view_local = blockIdx.z;
+    const int tw = 32 + point_size - 1, th = 8 + point_size - 1;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
+    const unsigned long long* src = corner + (size_t)view_local * Hc * Wc;
+    for (int t = threadIdx.x; t < tw * th; t += blockDim.x) {
+        const int cx = x0 + t % tw, cy = y0 + t / tw;
+        s_tile[t] = (cx < Wc && cy < Hc) ? src[(size_t)cy * Wc + cx] : ~0ull;
+    }
+    __syncthreads();
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int x = x0 + lx, y = y0 + ly;
+    if (x >= W || y >= H) return;
+    unsigned long long best = ~0ull;
+    for (int dy = 0; dy < point_size; dy++)
+        for (int dx = 0; dx < point_size; dx++) best = min(best, s_tile[(ly + dy) * tw + lx + dx]);
+    const size_t pix = ((size_t)(view_local + view_base) * H + y) * W + x;
+    uchar4 o;
+    float d = 0.0f;
+    if (best == ~0ull) {
+        o = make_uchar4(255, 255, 255, 0);
+    } else {
+        const uint32_t idx = (uint32_t)(best & 0xFFFFFFFFull);
+        o.x = rgb[3 * (size_t)idx + 0];
+        o.y = rgb[3 * (size_t)idx + 1];
+        o.z = rgb[3 * (size_t)idx + 2];
+        o.w = (o.x == 255 && o.y == 255 && o.z == 255) ? 0 : 255;  // convertToAlpha, Share_Data.hpp:771-784
+        d = __uint_as_float((uint32_t)(best >> 32));
+    }
+    reinterpret_cast<uchar4*>(rgba)[pix] = o;
+    if (depth) depth[pix] = d;
+}
+
+// =====================================================================================================
+// context
+// =====================================================================================================
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+enum KClass { K_CAST = 0, K_PROJECT, K_COUNT, K_GREEDY, K_SPLAT, K_RESOLVE, K_OTHER, K_NCLASS };
+
+struct TimedSpan {
+    int cls;
+    uint32_t launches;
+    cudaEvent_t a, b;
+};
+
+struct Id128 {
+    char b[128];
+};
+
+// NCCL is resolved at run time (dlopen) so the library has no link-time dependency on it.
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ Id128, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+}  // namespace
+
+struct prv_ctx {
+    int device = 0;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t mem_bytes = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int variant = PRV_VARIANT_AXIS;
+
+    // map
+    bool have_map = false;
+    DevMap map{};
+    double resolution = 0;
+    int lo[3] = {0, 0, 0}, n[3] = {0, 0, 0};
+    DevBuf d_bitmap, d_prefix, d_leaf_of_raster, d_keys, d_rgb;
+    std::vector<uint16_t> h_keys;
+
+    // camera
+    bool have_cam = false;
+    DevCam cam{};
+    prv_intrinsics intr{};
+
+    // views
+    uint32_t V = 0;
+    DevBuf d_views, d_view_ids, d_row_of_id;
+    std::vector<ViewConst> h_views;
+    std::vector<uint32_t> h_view_ids;
+    std::vector<uint32_t> h_row_of_id;  // view id -> row of the table the greedy runs over (kNone = absent)
+    uint32_t id_space = 0;
+
+    // cast outputs
+    DevBuf d_bitsets, d_counts, d_stats, d_pix_hit, d_pix_depth, d_mask, d_voxel_pix, d_voxel_hit, d_points;
+    int last_mode = -1;
+    bool have_pixels = false;
+    bool cast_done = false;
+    unsigned long long pix_stride = 0;
+    uint32_t mask_words = 0;
+
+    // greedy
+    DevBuf d_best, d_cov[2];
+    uint32_t greedy_max_iter = 0;
+    bool greedy_done = false;
+    // table the greedy runs over (local rows, or the all-gathered table)
+    const uint64_t* g_rows = nullptr;
+    uint32_t g_nrows = 0;
+    DevBuf d_all_rows, d_all_ids;
+    bool gathered = false;
+
+    // splat
+    DevBuf d_cloud_xyz, d_cloud_rgb, d_corner, d_rgba, d_depth_img;
+    uint64_t P = 0;
+    uint32_t rendered_views = 0;
+
+    // timing
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> free_events;
+    cudaEvent_t slots[16] = {};
+    DevBuf d_flush;
+
+    // counters (since prv_reset_counters)
+    uint64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+
+    // nccl
+    NcclApi nccl;
+    void* comm = nullptr;
+    int rank = 0, nranks = 1;
+};
+
+namespace {
+
+std::string g_create_error;
+
+int fail(prv_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c)
+        c->err = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) return fail(ctx, e_ == cudaErrorMemoryAllocation ? PRV_ERR_OOM : PRV_ERR_CUDA, \
+                                           "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int ensure(prv_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return PRV_OK;
+    if (b.p) {
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    if (bytes == 0) bytes = 16;
+    bytes = (bytes + 255) & ~(size_t)255;
+    CU(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return PRV_OK;
+}
+
+void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+cudaEvent_t get_event(prv_ctx* ctx) {
+    if (!ctx->free_events.empty()) {
+        cudaEvent_t e = ctx->free_events.back();
+        ctx->free_events.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct Span {
+    prv_ctx* ctx;
+    size_t idx;
+    bool on;
+    Span(prv_ctx* c, int cls, uint32_t launches) : ctx(c), idx(0), on(c->spans.size() < 65536) {
+        c->n_launches += launches;
+        if (!on) return;
+        TimedSpan s;
+        s.cls = cls;
+        s.launches = launches;
+        s.a = get_event(c);
+        s.b = get_event(c);
+        cudaEventRecord(s.a, c->stream);
+        idx = c->spans.size();
+        c->spans.push_back(s);
+    }
+    ~Span() {
+        if (on) cudaEventRecord(ctx->spans[idx].b, ctx->stream);
+    }
+};
+
+cudaError_t h2d(prv_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    ctx->h2d_bytes += bytes;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+}
+cudaError_t d2h(prv_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    ctx->d2h_bytes += bytes;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+}
+
+template <typename T>
+T* ptr(const DevBuf& b) {
+    return reinterpret_cast<T*>(b.p);
+}
+
+uint32_t words_for(uint32_t n_occ) {
+    uint32_t w = (n_occ + 63) / 64;
+    if (w == 0) w = 1;
+    return (w + 1) & ~1u;
+}
+
+// castRay's d^2 for a key triple, host copy of dist_sq_at (float terms, double accumulation)
+double host_dist_sq(const float origin[3], double res, const int k[3]) {
+    double acc = 0.0;
+    for (int j = 0; j < 3; j++) {
+        const float e = (float)prv::key_to_coord(k[j], res);
+        const float df = e - origin[j];
+        acc += (double)(df * df);
+    }
+    return acc;
+}
+
+// per-view constants: snapped origin (main.cpp:112-114), inverse pose (main.cpp:244), fast-path proof
+void make_view_const(const prv_ctx* ctx, const double* pose_world, const double* init_pos, uint32_t id, ViewConst& vc) {
+    const prv::Matrix4d pw = prv::Matrix4d::FromRowMajor(pose_world);
+    const prv::Matrix4d inv = pw.inverse();
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) {
+            vc.pose[4 * r + c] = pw(r, c);
+            vc.inv[4 * r + c] = inv(r, c);
+        }
+    vc.flags = 0;
+    vc.view_id = id;
+    const double rf = 1.0 / ctx->resolution;
+    uint16_t k[3] = {0, 0, 0};
+    bool ok = true;
+    for (int a = 0; a < 3; a++) ok = prv::coord_to_key_checked(init_pos[a], rf, k[a]) && ok;
+    for (int a = 0; a < 3; a++) {
+        vc.okey[a] = k[a];
+        vc.origin[a] = ok ? (float)prv::key_to_coord(k[a], ctx->resolution) : 0.0f;
+    }
+    if (!ok) return;
+    vc.flags |= kViewInMap;
+    // castRay re-derives current_key from the float origin; it is the same key (|error| << half a voxel) but recompute literally
+    for (int a = 0; a < 3; a++) {
+        uint16_t kk;
+        if (prv::coord_to_key_checked((double)vc.origin[a], rf, kk)) vc.okey[a] = kk;
+    }
+    // origin voxel occupied?
+    bool inside = true;
+    for (int a = 0; a < 3; a++) inside = inside && vc.okey[a] >= ctx->lo[a] && vc.okey[a] < ctx->lo[a] + ctx->n[a];
+    if (inside && ctx->n[0] > 0) {
+        const uint64_t code = prv::morton_code((uint16_t)vc.okey[0], (uint16_t)vc.okey[1], (uint16_t)vc.okey[2]);
+        const size_t N = ctx->h_keys.size() / 3;
+        size_t lo = 0, hi = N;
+        while (lo < hi) {
+            const size_t mid = (lo + hi) / 2;
+            const uint64_t cm = prv::morton_code(ctx->h_keys[3 * mid], ctx->h_keys[3 * mid + 1], ctx->h_keys[3 * mid + 2]);
+            if (cm < code) lo = mid + 1; else hi = mid;
+        }
+        if (lo < N && prv::morton_code(ctx->h_keys[3 * lo], ctx->h_keys[3 * lo + 1], ctx->h_keys[3 * lo + 2]) == code) vc.flags |= kViewInObject;
+    }
+    // fast path proof: while a ray can still hit, every key it visits lies in the box spanned by the origin key and the
+    // AABB grown by one voxel; the float d^2 terms are monotone in |key - origin key| per axis, so the corner sum bounds
+    // every d^2 the reference would test.  Also no key-overflow test can fire inside [1, 65534].
+    bool fast = ctx->n[0] > 0;
+    for (int a = 0; a < 3 && fast; a++) fast = ctx->lo[a] >= 2 && ctx->lo[a] + ctx->n[a] <= 65533;
+    if (fast && ctx->cam.max_range > 0.0) {
+        double acc = 0.0;
+        for (int a = 0; a < 3; a++) {
+            int kl[3] = {vc.okey[0], vc.okey[1], vc.okey[2]}, kh[3] = {vc.okey[0], vc.okey[1], vc.okey[2]};
+            kl[a] = ctx->lo[a] - 1;
+            kh[a] = ctx->lo[a] + ctx->n[a];
+            // per-axis term = d^2 with the other two axes at the origin key (their terms are exactly 0)
+            const double tl = host_dist_sq(vc.origin, ctx->resolution, kl);
+            const double th = host_dist_sq(vc.origin, ctx->resolution, kh);
+            acc += std::max(tl, th);
+        }
+        // acc >= any double-accumulated d^2 in the box up to 2 roundings; keep a 1e-9 relative guard band
+        fast = acc * (1.0 + 1e-9) <= ctx->cam.max_range_sq;
+    }
+    if (fast) vc.flags |= kViewFastOk;
+}
+
+int upload_views(prv_ctx* ctx, const double* pose_world, const double* init_pos, uint32_t V) {
+    if (!ctx->have_map || !ctx->have_cam) return fail(ctx, PRV_ERR_INVALID, "prv_set_views: call prv_set_map and prv_set_camera first");
+    if (!pose_world || !init_pos || V == 0) return fail(ctx, PRV_ERR_INVALID, "prv_set_views: null/empty input");
+    ctx->h_views.resize(V);
+    const bool ids_ok = ctx->h_view_ids.size() == V;
+    for (uint32_t v = 0; v < V; v++) make_view_const(ctx, pose_world + 16 * (size_t)v, init_pos + 3 * (size_t)v, ids_ok ? ctx->h_view_ids[v] : v, ctx->h_views[v]);
+    if (!ids_ok) {
+        ctx->h_view_ids.resize(V);
+        for (uint32_t v = 0; v < V; v++) ctx->h_view_ids[v] = v;
+    }
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_views, sizeof(ViewConst) * (size_t)V))) return rc;
+    CU(h2d(ctx, ctx->d_views.p, ctx->h_views.data(), sizeof(ViewConst) * (size_t)V));
+    // id tables for the greedy
+    uint32_t max_id = 0;
+    for (uint32_t v = 0; v < V; v++) max_id = std::max(max_id, ctx->h_view_ids[v]);
+    std::vector<uint32_t>& row_of_id = ctx->h_row_of_id;
+    row_of_id.assign((size_t)max_id + 1, kNone);
+    for (uint32_t v = 0; v < V; v++) row_of_id[ctx->h_view_ids[v]] = v;
+    ctx->id_space = max_id + 1;
+    if ((rc = ensure(ctx, ctx->d_view_ids, 4 * (size_t)V))) return rc;
+    if ((rc = ensure(ctx, ctx->d_row_of_id, 4 * (size_t)ctx->id_space))) return rc;
+    CU(h2d(ctx, ctx->d_view_ids.p, ctx->h_view_ids.data(), 4 * (size_t)V));
+    CU(h2d(ctx, ctx->d_row_of_id.p, row_of_id.data(), 4 * (size_t)ctx->id_space));
+    CU(cudaStreamSynchronize(ctx->stream));  // host staging vectors go out of scope
+    ctx->V = V;
+    ctx->cast_done = false;
+    ctx->greedy_done = false;
+    ctx->gathered = false;
+    return PRV_OK;
+}
+
+template <int VARIANT>
+void launch_cast(prv_ctx* ctx, const CastParams& p, bool masked, dim3 grid) {
+    if (masked)
+        raycast_kernel<VARIANT, true><<<grid, 256, 0, ctx->stream>>>(p);
+    else
+        raycast_kernel<VARIANT, false><<<grid, 256, 0, ctx->stream>>>(p);
+}
+
+int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
+    if (!ctx->have_map || !ctx->have_cam || ctx->V == 0) return fail(ctx, PRV_ERR_INVALID, "prv_cast: map, camera and views must be set");
+    if (mode != PRV_MODE_VOXEL && mode != PRV_MODE_DENSE) return fail(ctx, PRV_ERR_INVALID, "prv_cast: bad mode %d", mode);
+    const uint32_t V = ctx->V;
+    const uint32_t words = ctx->map.words64;
+    const int W = ctx->cam.W, H = ctx->cam.H;
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_bitsets, (size_t)V * words * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->d_counts, (size_t)V * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_stats, 4 * 8))) return rc;
+    CU(cudaMemsetAsync(ctx->d_bitsets.p, 0, (size_t)V * words * 8, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_stats.p, 0, 4 * 8, ctx->stream));
+
+    CastParams p{};
+    p.map = ctx->map;
+    p.cam = ctx->cam;
+    p.views = ptr<ViewConst>(ctx->d_views);
+    p.bitsets32 = ptr<uint32_t>(ctx->d_bitsets);
+    p.stats = ptr<unsigned long long>(ctx->d_stats);
+    const bool voxel = mode == PRV_MODE_VOXEL;
+    p.GW = voxel ? W + 1 : W;
+    p.GH = voxel ? H + 1 : H;
+    ctx->pix_stride = (unsigned long long)p.GW * p.GH;
+    p.pix_stride = ctx->pix_stride;
+    const bool pixels = voxel || want_pixels;
+    if (pixels) {
+        if ((rc = ensure(ctx, ctx->d_pix_hit, (size_t)V * ctx->pix_stride * 4))) return rc;
+        p.pix_hit = ptr<uint32_t>(ctx->d_pix_hit);
+        if (!voxel) {
+            if ((rc = ensure(ctx, ctx->d_pix_depth, (size_t)V * ctx->pix_stride * 4))) return rc;
+            p.pix_depth = ptr<float>(ctx->d_pix_depth);
+        }
+    }
+    if (voxel) {
+        ctx->mask_words = (uint32_t)((ctx->pix_stride + 31) / 32);
+        p.mask_words = ctx->mask_words;
+        if ((rc = ensure(ctx, ctx->d_mask, (size_t)V * ctx->mask_words * 4))) return rc;
+        if ((rc = ensure(ctx, ctx->d_voxel_pix, (size_t)V * ctx->map.n_occ * 4))) return rc;
+        CU(cudaMemsetAsync(ctx->d_mask.p, 0, (size_t)V * ctx->mask_words * 4, ctx->stream));
+        p.mask = ptr<uint32_t>(ctx->d_mask);
+    }
+    const uint32_t tiles = (uint32_t)(((p.GW + 31) / 32) * ((p.GH + 7) / 8));
+    for (uint32_t vb = 0; vb < V; vb += 32768) {
+        const uint32_t vn = std::min<uint32_t>(32768, V - vb);
+        if (voxel) {
+            Span s(ctx, K_PROJECT, 1);
+            project_voxels_kernel<<<dim3((ctx->map.n_occ + 255) / 256, vn), 256, 0, ctx->stream>>>(
+                ctx->map, ctx->cam, ptr<ViewConst>(ctx->d_views), vb, ptr<uint32_t>(ctx->d_mask), ctx->mask_words, ptr<uint32_t>(ctx->d_voxel_pix));
+        }
+        p.view_base = vb;
+        {
+            Span s(ctx, K_CAST, 1);
+            const dim3 grid(tiles, vn);
+            if (ctx->variant == PRV_VARIANT_PLAIN)
+                launch_cast<PRV_VARIANT_PLAIN>(ctx, p, voxel, grid);
+            else if (ctx->variant == PRV_VARIANT_FAST)
+                launch_cast<PRV_VARIANT_FAST>(ctx, p, voxel, grid);
+            else
+                launch_cast<PRV_VARIANT_AXIS>(ctx, p, voxel, grid);
+        }
+    }
+    {
+        Span s(ctx, K_COUNT, 1);
+        popcount_rows_kernel<<<V, 256, 0, ctx->stream>>>(ptr<uint64_t>(ctx->d_bitsets), words, ptr<uint32_t>(ctx->d_counts));
+    }
+    CU(cudaGetLastError());
+    ctx->last_mode = mode;
+    ctx->have_pixels = pixels;
+    ctx->cast_done = true;
+    ctx->greedy_done = false;
+    ctx->gathered = false;
+    ctx->g_rows = ptr<uint64_t>(ctx->d_bitsets);
+    ctx->g_nrows = V;
+    return PRV_OK;
+}
+
+int greedy_impl(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter) {
+    if (!ctx->cast_done) return fail(ctx, PRV_ERR_INVALID, "prv_greedy: no coverage bitsets resident (call prv_cast_* first)");
+    if (first_view >= ctx->id_space) return fail(ctx, PRV_ERR_INVALID, "prv_greedy: first_view %u out of range", first_view);
+    const uint32_t words = ctx->map.words64;
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_best, 8 * ((size_t)max_iter + 2)))) return rc;
+    if ((rc = ensure(ctx, ctx->d_cov[0], 8 * (size_t)words))) return rc;
+    if ((rc = ensure(ctx, ctx->d_cov[1], 8 * (size_t)words))) return rc;
+    CU(cudaMemsetAsync(ctx->d_best.p, 0, 8 * ((size_t)max_iter + 2), ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_cov[0].p, 0, 8 * (size_t)words, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_cov[1].p, 0, 8 * (size_t)words, ctx->stream));
+    const uint32_t* ids = ctx->gathered ? ptr<uint32_t>(ctx->d_all_ids) : ptr<uint32_t>(ctx->d_view_ids);
+    const uint32_t* row_of_id = ptr<uint32_t>(ctx->d_row_of_id);
+    // row index of first_view in the active table
+    const uint32_t first_row = ctx->h_row_of_id[first_view];
+    if (first_row == kNone) return fail(ctx, PRV_ERR_INVALID, "prv_greedy: first_view %u is not a resident view id", first_view);
+    Span s(ctx, K_GREEDY, max_iter + 2);
+    greedy_init_kernel<<<1, 256, 0, ctx->stream>>>(ctx->g_rows, words, first_row, first_view, ptr<unsigned long long>(ctx->d_best));
+    for (uint32_t k = 1; k <= max_iter + 1; k++) {
+        const int cover_only = k == max_iter + 1;
+        greedy_iter_kernel<<<cover_only ? 1 : ctx->g_nrows, 256, 0, ctx->stream>>>(
+            ctx->g_rows, words, ids, row_of_id, k, ptr<unsigned long long>(ctx->d_best), ptr<uint64_t>(ctx->d_cov[(k - 1) & 1]),
+            ptr<uint64_t>(ctx->d_cov[k & 1]), cover_only);
+    }
+    CU(cudaGetLastError());
+    ctx->greedy_max_iter = max_iter;
+    ctx->greedy_done = true;
+    return PRV_OK;
+}
+
+int render_impl(prv_ctx* ctx, uint32_t V, int point_size, bool want_depth) {
+    if (!ctx->have_cam || ctx->P == 0 || ctx->V < V || V == 0) return fail(ctx, PRV_ERR_INVALID, "prv_render: camera, cloud and views must be set");
+    if (point_size < 1 || point_size > 32) return fail(ctx, PRV_ERR_INVALID, "prv_render: point_size %d out of [1,32]", point_size);
+    const int W = ctx->cam.W, H = ctx->cam.H;
+    const int Wc = W + point_size - 1, Hc = H + point_size - 1;
+    const size_t corner_bytes = (size_t)Wc * Hc * 8;
+    // keep the corner buffers of one chunk around L2 size
+    uint32_t chunk = (uint32_t)std::max<size_t>(1, (size_t)(96u << 20) / corner_bytes);
+    chunk = std::min<uint32_t>(std::min<uint32_t>(chunk, V), 65535u);
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_corner, corner_bytes * chunk))) return rc;
+    if ((rc = ensure(ctx, ctx->d_rgba, (size_t)V * W * H * 4))) return rc;
+    if (want_depth && (rc = ensure(ctx, ctx->d_depth_img, (size_t)V * W * H * 4))) return rc;
+    const float focal = prv_splat_focal(&ctx->intr);
+    const size_t smem = (size_t)(32 + point_size - 1) * (8 + point_size - 1) * 8;
+    for (uint32_t vb = 0; vb < V; vb += chunk) {
+        const uint32_t vn = std::min(chunk, V - vb);
+        CU(cudaMemsetAsync(ctx->d_corner.p, 0xFF, corner_bytes * vn, ctx->stream));
+        {
+            Span s(ctx, K_SPLAT, 1);
+            splat_points_kernel<<<dim3((unsigned)((ctx->P + 255) / 256), vn), 256, 0, ctx->stream>>>(
+                ptr<float>(ctx->d_cloud_xyz), ctx->P, ctx->cam, ptr<ViewConst>(ctx->d_views), vb, focal, point_size,
+                ptr<unsigned long long>(ctx->d_corner), Wc, Hc);
+        }
+        {
+            Span s(ctx, K_RESOLVE, 1);
+            splat_resolve_kernel<<<dim3((W + 31) / 32, (H + 7) / 8, vn), 256, smem, ctx->stream>>>(
+                ptr<unsigned long long>(ctx->d_corner), Wc, Hc, W, H, point_size, ptr<uint8_t>(ctx->d_cloud_rgb), ptr<uint8_t>(ctx->d_rgba),
+                want_depth ? ptr<float>(ctx->d_depth_img) : nullptr, vb);
+        }
+    }
+    CU(cudaGetLastError());
+    ctx->rendered_views = V;
+    return PRV_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* prv_last_error(const prv_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int prv_create(prv_ctx** out, int device) {
+    if (!out) return fail(nullptr, PRV_ERR_INVALID, "prv_create: null out pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, PRV_ERR_NO_DEVICE, "prv_create: no CUDA device (%s); libprv_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, PRV_ERR_INVALID, "prv_create: device %d out of range (0..%d)", device, count - 1);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return fail(nullptr, PRV_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, PRV_ERR_NO_DEVICE, "prv_create: device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(nullptr, PRV_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    prv_ctx* ctx = new prv_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->mem_bytes = prop.totalGlobalMem;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, PRV_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    for (auto& s : ctx->slots) cudaEventCreate(&s);
+    *out = ctx;
+    return PRV_OK;
+}
+
+void prv_destroy(prv_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    prv_comm_destroy(ctx);
+    DevBuf* bufs[] = {&ctx->d_bitmap, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
+                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
+                      &ctx->d_voxel_pix, &ctx->d_voxel_hit, &ctx->d_points, &ctx->d_best, &ctx->d_cov[0], &ctx->d_cov[1], &ctx->d_all_rows,
+                      &ctx->d_all_ids, &ctx->d_cloud_xyz, &ctx->d_cloud_rgb, &ctx->d_corner, &ctx->d_rgba, &ctx->d_depth_img, &ctx->d_flush};
+    for (DevBuf* b : bufs) release(*b);
+    for (auto& s : ctx->spans) {
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    for (auto& e : ctx->free_events) cudaEventDestroy(e);
+    for (auto& s : ctx->slots) cudaEventDestroy(s);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int prv_device_info(prv_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, uint64_t* mem_bytes) {
+    if (!ctx) return PRV_ERR_INVALID;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (mem_bytes) *mem_bytes = ctx->mem_bytes;
+    return PRV_OK;
+}
+
+int prv_sync(prv_ctx* ctx) {
+    if (!ctx) return PRV_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PRV_OK;
+}
+
+int prv_set_variant(prv_ctx* ctx, int variant) {
+    if (!ctx) return PRV_ERR_INVALID;
+    if (variant < PRV_VARIANT_PLAIN || variant > PRV_VARIANT_AXIS) return fail(ctx, PRV_ERR_INVALID, "prv_set_variant: unknown variant %d", variant);
+    ctx->variant = variant;
+    return PRV_OK;
+}
+
+int prv_set_map(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, uint32_t N, double resolution) {
+    if (!ctx) return PRV_ERR_INVALID;
+    if (!keys || N == 0 || !(resolution > 0)) return fail(ctx, PRV_ERR_INVALID, "prv_set_map: null/empty map or bad resolution");
+    CU(cudaSetDevice(ctx->device));
+    // leaf order must be strictly ascending Morton (begin_leafs order, no duplicates)
+    uint64_t prev = 0;
+    int lo[3] = {65536, 65536, 65536}, hi[3] = {-1, -1, -1};
+    for (uint32_t i = 0; i < N; i++) {
+        const uint64_t c = prv::morton_code(keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]);
+        if (i && c <= prev) return fail(ctx, PRV_ERR_INVALID, "prv_set_map: keys are not in strict leaf (Morton) order at index %u", i);
+        prev = c;
+        for (int a = 0; a < 3; a++) {
+            lo[a] = std::min(lo[a], (int)keys[3 * i + a]);
+            hi[a] = std::max(hi[a], (int)keys[3 * i + a]);
+        }
+    }
+    int n[3];
+    for (int a = 0; a < 3; a++) n[a] = hi[a] - lo[a] + 1;
+    const int wx = (n[0] + 31) / 32;
+    const size_t nwords = (size_t)wx * n[1] * n[2];
+    if (nwords > ((size_t)1 << 31)) return fail(ctx, PRV_ERR_UNSUPPORTED, "prv_set_map: occupancy AABB %dx%dx%d too large for a dense bitmap", n[0], n[1], n[2]);
+    std::vector<uint32_t> bitmap(nwords, 0u), prefix(nwords, 0u), leaf_of_raster(N, 0u);
+    auto word_of = [&](const uint16_t* k) { return ((size_t)(k[2] - lo[2]) * n[1] + (size_t)(k[1] - lo[1])) * wx + (size_t)((k[0] - lo[0]) >> 5); };
+    for (uint32_t i = 0; i < N; i++) bitmap[word_of(keys + 3 * i)] |= 1u << ((keys[3 * i] - lo[0]) & 31);
+    uint32_t run = 0;
+    for (size_t w = 0; w < nwords; w++) {
+        prefix[w] = run;
+        run += (uint32_t)__builtin_popcount(bitmap[w]);
+    }
+    for (uint32_t i = 0; i < N; i++) {
+        const size_t w = word_of(keys + 3 * i);
+        const uint32_t bit = (keys[3 * i] - lo[0]) & 31;
+        leaf_of_raster[prefix[w] + (uint32_t)__builtin_popcount(bitmap[w] & ((1u << bit) - 1u))] = i;
+    }
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_bitmap, nwords * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_prefix, nwords * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_leaf_of_raster, (size_t)N * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_keys, (size_t)N * 6))) return rc;
+    if ((rc = ensure(ctx, ctx->d_rgb, (size_t)N * 3))) return rc;
+    CU(h2d(ctx, ctx->d_bitmap.p, bitmap.data(), nwords * 4));
+    CU(h2d(ctx, ctx->d_prefix.p, prefix.data(), nwords * 4));
+    CU(h2d(ctx, ctx->d_leaf_of_raster.p, leaf_of_raster.data(), (size_t)N * 4));
+    CU(h2d(ctx, ctx->d_keys.p, keys, (size_t)N * 6));
+    if (rgb)
+        CU(h2d(ctx, ctx->d_rgb.p, rgb, (size_t)N * 3));
+    else
+        CU(cudaMemsetAsync(ctx->d_rgb.p, 0, (size_t)N * 3, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->h_keys.assign(keys, keys + (size_t)N * 3);
+    ctx->resolution = resolution;
+    for (int a = 0; a < 3; a++) {
+        ctx->lo[a] = lo[a];
+        ctx->n[a] = n[a];
+        ctx->map.lo[a] = lo[a];
+        ctx->map.n[a] = n[a];
+    }
+    ctx->map.resolution = resolution;
+    ctx->map.wx = wx;
+    ctx->map.n_occ = N;
+    ctx->map.words64 = words_for(N);
+    ctx->map.bitmap = ptr<uint32_t>(ctx->d_bitmap);
+    ctx->map.prefix = ptr<uint32_t>(ctx->d_prefix);
+    ctx->map.leaf_of_raster = ptr<uint32_t>(ctx->d_leaf_of_raster);
+    ctx->map.keys = ptr<uint16_t>(ctx->d_keys);
+    ctx->map.rgb = ptr<uint8_t>(ctx->d_rgb);
+    ctx->have_map = true;
+    ctx->V = 0;
+    ctx->cast_done = false;
+    ctx->greedy_done = false;
+    return PRV_OK;
+}
+
+int prv_set_camera(prv_ctx* ctx, const prv_intrinsics* intr, double max_range) {
+    if (!ctx) return PRV_ERR_INVALID;
+    if (!intr || intr->width <= 0 || intr->height <= 0) return fail(ctx, PRV_ERR_INVALID, "prv_set_camera: bad intrinsics");
+    if (intr->model == 3 || intr->model == 5)
+        return fail(ctx, PRV_ERR_UNSUPPORTED,
+                    "prv_set_camera: distortion model %d (F-Theta / Kannala-Brandt) needs atan/tan and cannot be bit-exact on the GPU", intr->model);
+    if (intr->model < 0 || intr->model > 5) return fail(ctx, PRV_ERR_INVALID, "prv_set_camera: unknown distortion model %d", intr->model);
+    if (intr->model == 1)
+        return fail(ctx, PRV_ERR_UNSUPPORTED, "prv_set_camera: model 1 (MODIFIED_BROWN_CONRADY) cannot be deprojected (reference asserts, Share_Data.hpp:142)");
+    if ((long long)(intr->width + 1) * (intr->height + 1) > (1ll << 31)) return fail(ctx, PRV_ERR_UNSUPPORTED, "prv_set_camera: image too large");
+    ctx->intr = *intr;
+    ctx->cam.W = intr->width;
+    ctx->cam.H = intr->height;
+    ctx->cam.ppx = intr->ppx;
+    ctx->cam.ppy = intr->ppy;
+    ctx->cam.fx = intr->fx;
+    ctx->cam.fy = intr->fy;
+    ctx->cam.model = intr->model;
+    for (int i = 0; i < 5; i++) ctx->cam.c[i] = intr->coeffs[i];
+    ctx->cam.max_range = max_range;
+    ctx->cam.max_range_sq = max_range * max_range;
+    ctx->have_cam = true;
+    ctx->V = 0;  // per-view fast-path proofs depend on max_range
+    ctx->cast_done = false;
+    return PRV_OK;
+}
+
+int prv_set_view_ids(prv_ctx* ctx, const uint32_t* ids, uint32_t V) {
+    if (!ctx) return PRV_ERR_INVALID;
+    if (!ids) {
+        ctx->h_view_ids.clear();
+        return PRV_OK;
+    }
+    ctx->h_view_ids.assign(ids, ids + V);
+    return PRV_OK;
+}
+
+int prv_set_views(prv_ctx* ctx, const double* pose_world, const double* init_pos, uint32_t V) {
+    if (!ctx) return PRV_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->h_view_ids.size() != V) ctx->h_view_ids.clear();
+    return upload_views(ctx, pose_world, init_pos, V);
+}
+
+uint32_t prv_full_voxels(const prv_ctx* ctx) { return ctx && ctx->have_map ? ctx->map.n_occ : 0; }
+uint32_t prv_bitset_words(const prv_ctx* ctx) { return ctx && ctx->have_map ? ctx->map.words64 : 0; }
+uint32_t prv_num_views(const prv_ctx* ctx) { return ctx ? ctx->V : 0; }
+
+int prv_cast_async(prv_ctx* ctx, int mode, int want_pixels) {
+    if (!ctx) return PRV_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    return cast_impl(ctx, mode, want_pixels);
+}
+
+int prv_greedy_async(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter) {
+    if (!ctx) return PRV_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    return greedy_impl(ctx, first_view, max_iter);
+}
+
+int prv_get_bitsets(prv_ctx* ctx, uint64_t* out) {
+    if (!ctx || !out) return PRV_ERR_INVALID;
+    if (!ctx->cast_done) return fail(ctx, PRV_ERR_INVALID, "prv_get_bitsets: nothing cast yet");
+    CU(cudaSetDevice(ctx->device));
+    CU(d2h(ctx, out, ctx->d_bitsets.p, (size_t)ctx->V * ctx->map.words64 * 8));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PRV_OK;
+}
+
+int prv_get_coverage_counts(prv_ctx* ctx, uint32_t* out) {
+    if (!ctx || !out) return PRV_ERR_INVALID;
+    if (!ctx->cast_done) return fail(ctx, PRV_ERR_INVALID, "prv_get_coverage_counts: nothing cast yet");
+    CU(cudaSetDevice(ctx->device));
+    CU(d2h(ctx, out, ctx->d_counts.p, (size_t)ctx->V * 4));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PRV_OK;
+}
+
+int prv_get_hit_rank(prv_ctx* ctx, uint32_t view_begin, uint32_t view_count, uint32_t* out) {
+    if (!ctx || !out) return PRV_ERR_INVALID;
+    if (!ctx->cast_done || !ctx->have_pixels) return fail(ctx, PRV_ERR_INVALID, "prv_get_hit_rank: last cast did not keep per-pixel results");
+    if ((uint64_t)view_begin + view_count > ctx->V) return fail(ctx, PRV_ERR_INVALID, "prv_get_hit_rank: view range out of bounds");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->last_mode == PRV_MODE_DENSE) {
+        CU(d2h(ctx, out, ptr<uint32_t>(ctx->d_pix_hit) + (size_t)view_begin * ctx->pix_stride, (size_t)view_count * ctx->pix_stride * 4));
+    } else {
+        const uint32_t N = ctx->map.n_occ;
+        int rc;
+        if ((rc = ensure(ctx, ctx->d_voxel_hit, (size_t)view_count * N * 4))) return rc;
+        {
+            Span s(ctx, K_OTHER, 1);
+            gather_voxel_hits_kernel<<<dim3((N + 255) / 256, view_count), 256, 0, ctx->stream>>>(
+                N, ptr<uint32_t>(ctx->d_voxel_pix) + (size_t)view_begin * N, ptr<uint32_t>(ctx->d_pix_hit) + (size_t)view_begin * ctx->pix_stride,
+                ctx->pix_stride, ptr<uint32_t>(ctx->d_voxel_hit));
+        }
+        CU(cudaGetLastError());
+        CU(d2h(ctx, out, ctx->d_voxel_hit.p, (size_t)view_count * N * 4));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PRV_OK;
+}
+
+int prv_get_depth(prv_ctx* ctx, uint32_t view_begin, uint32_t view_count, float* out) {
+    if (!ctx || !out) return PRV_ERR_INVALID;
+    if (!ctx->cast_done || !ctx->have_pixels || ctx->last_mode != PRV_MODE_DENSE)
+        return fail(ctx, PRV_ERR_INVALID, "prv_get_depth: last cast was not a dense cast with per-pixel results");
+    if ((uint64_t)view_begin + view_count > ctx->V) return fail(ctx, PRV_ERR_INVALID, "prv_get_depth: view range out of bounds");
+    CU(cudaSetDevice(ctx->device));
+    CU(d2h(ctx, out, ptr<float>(ctx->d_pix_depth) + (size_t)view_begin * ctx->pix_stride, (size_t)view_count * ctx->pix_stride * 4));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PRV_OK;
+}
+
+int prv_get_greedy(prv_ctx* ctx, uint32_t* seq, uint32_t* gains, uint32_t* n_out, uint64_t* covered_out) {
+    if (!ctx || !seq || !gains || !n_out) return PRV_ERR_INVALID;
+    if (!ctx->greedy_done) return fail(ctx, PRV_ERR_INVALID, "prv_get_greedy: prv_greedy_async has not run");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<unsigned long long> best((size_t)ctx->greedy_max_iter + 2);
+    CU(d2h(ctx, best.data(), ctx->d_best.p, 8 * best.size()));
+    CU(cudaStreamSynchronize(ctx->stream));
+    uint32_t n = 0;
+    for (uint32_t k = 0; k <= ctx->greedy_max_iter; k++) {
+        const uint32_t g = (uint32_t)(best[k] >> 32);
+        if (k > 0 && g == 0) break;
+        seq[n] = 0xFFFFFFFFu - (uint32_t)(best[k] & 0xFFFFFFFFull);
+        gains[n] = g;
+        n++;
+    }
+    *n_out = n;
+    if (covered_out) {
+        CU(d2h(ctx, covered_out, ctx->d_cov[n & 1].p, 8 * (size_t)ctx->map.words64));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return PRV_OK;
+}
+
+int prv_get_cast_stats(prv_ctx* ctx, prv_cast_stats* out) {
+    if (!ctx || !out) return PRV_ERR_INVALID;
+    if (!ctx->cast_done) return fail(ctx, PRV_ERR_INVALID, "prv_get_cast_stats: nothing cast yet");
+    CU(cudaSetDevice(ctx->device));
+    unsigned long long s[4];
+    CU(d2h(ctx, s, ctx->d_stats.p, sizeof(s)));
+    CU(cudaStreamSynchronize(ctx->stream));
+    out->rays = s[0];
+    out->probes_in = s[1];
+    out->hits = s[2];
+    out->steps = s[3];
+    return PRV_OK;
+}
+
+int prv_cast_views(prv_ctx* ctx, const double* pose_world, const double* init_pos, uint32_t V, int mode, uint64_t* bitsets_out,
+                   uint32_t* coverage_count_out, uint32_t* hit_rank_out, float* depth_out) {
+    if (!ctx) return PRV_ERR_INVALID;
+    int rc;
+    if ((rc = prv_set_views(ctx, pose_world, init_pos, V))) return rc;
+    if ((rc = cast_impl(ctx, mode, hit_rank_out || depth_out))) return rc;
+    if (bitsets_out && (rc = prv_get_bitsets(ctx, bitsets_out))) return rc;
+    if (coverage_count_out && (rc = prv_get_coverage_counts(ctx, coverage_count_out))) return rc;
+    if (hit_rank_out && (rc = prv_get_hit_rank(ctx, 0, V, hit_rank_out))) return rc;
+    if (depth_out && (rc = prv_get_depth(ctx, 0, V, depth_out))) return rc;
+    return prv_sync(ctx);
+}
+
+int prv_precept(prv_ctx* ctx, const double pose_world[16], const double init_pos[3], prv_point_xyzrgb* points_out, int* view_in_map_out) {
+    if (!ctx || !points_out) return PRV_ERR_INVALID;
+    int rc;
+    ctx->h_view_ids.clear();
+    if ((rc = prv_set_views(ctx, pose_world, init_pos, 1))) return rc;
+    if (view_in_map_out) *view_in_map_out = (ctx->h_views[0].flags & kViewInMap) ? 1 : 0;
+    if ((rc = cast_impl(ctx, PRV_MODE_VOXEL, 0))) return rc;
+    const uint32_t N = ctx->map.n_occ;
+    if ((rc = ensure(ctx, ctx->d_voxel_hit, (size_t)N * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_points, (size_t)N * sizeof(prv_point_xyzrgb)))) return rc;
+    {
+        Span s(ctx, K_OTHER, 2);
+        gather_voxel_hits_kernel<<<dim3((N + 255) / 256, 1), 256, 0, ctx->stream>>>(N, ptr<uint32_t>(ctx->d_voxel_pix), ptr<uint32_t>(ctx->d_pix_hit),
+                                                                                   ctx->pix_stride, ptr<uint32_t>(ctx->d_voxel_hit));
+        precept_points_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(ctx->map, ptr<uint32_t>(ctx->d_voxel_hit), ptr<prv_point_xyzrgb>(ctx->d_points));
+    }
+    CU(cudaGetLastError());
+    CU(d2h(ctx, points_out, ctx->d_points.p, (size_t)N * sizeof(prv_point_xyzrgb)));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PRV_OK;
+}
+
+int prv_greedy(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter, uint32_t* seq, uint32_t* gains, uint32_t* n_out) {
+    if (!ctx) return PRV_ERR_INVALID;
+    int rc;
+    if ((rc = prv_greedy_async(ctx, first_view, max_iter))) return rc;
+    return prv_get_greedy(ctx, seq, gains, n_out, nullptr);
+}
+
+int prv_set_cloud(prv_ctx* ctx, const float* xyz, const uint8_t* rgb, uint64_t P) {
+    if (!ctx) return PRV_ERR_INVALID;
+    if (!xyz || !rgb || P == 0 || P > 0xFFFFFFFEull) return fail(ctx, PRV_ERR_INVALID, "prv_set_cloud: null/empty cloud (or more than 2^32-2 points)");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_cloud_xyz, P * 12))) return rc;
+    if ((rc = ensure(ctx, ctx->d_cloud_rgb, P * 3))) return rc;
+    CU(h2d(ctx, ctx->d_cloud_xyz.p, xyz, P * 12));
+    CU(h2d(ctx, ctx->d_cloud_rgb.p, rgb, P * 3));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->P = P;
+    return PRV_OK;
+}
+
+int prv_render_async(prv_ctx* ctx, uint32_t V, int point_size) {
+    if (!ctx) return PRV_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    return render_impl(ctx, V, point_size, true);
+}
+
+int prv_render_views(prv_ctx* ctx, const double* pose_world, uint32_t V, int point_size, uint8_t* rgba_out, float* depth_out) {
+    if (!ctx || !pose_world || !rgba_out) return PRV_ERR_INVALID;
+    if (!ctx->have_cam) return fail(ctx, PRV_ERR_INVALID, "prv_render_views: camera not set");
+    CU(cudaSetDevice(ctx->device));
+    // only the inverse pose is needed; build view constants without a map dependency
+    std::vector<ViewConst> vcs(V);
+    for (uint32_t v = 0; v < V; v++) {
+        const prv::Matrix4d pw = prv::Matrix4d::FromRowMajor(pose_world + 16 * (size_t)v);
+        const prv::Matrix4d inv = pw.inverse();
+        std::memset(&vcs[v], 0, sizeof(ViewConst));
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 4; c++) {
+                vcs[v].pose[4 * r + c] = pw(r, c);
+                vcs[v].inv[4 * r + c] = inv(r, c);
+            }
+        vcs[v].view_id = v;
+    }
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_views, sizeof(ViewConst) * (size_t)V))) return rc;
+    CU(h2d(ctx, ctx->d_views.p, vcs.data(), sizeof(ViewConst) * (size_t)V));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const uint32_t keepV = ctx->V;
+    ctx->V = V;
+    rc = render_impl(ctx, V, point_size, depth_out != nullptr);
+    ctx->V = 0;  // resident cast views were overwritten
+    (void)keepV;
+    ctx->cast_done = false;
+    if (rc) return rc;
+    const size_t px = (size_t)V * ctx->cam.W * ctx->cam.H;
+    CU(d2h(ctx, rgba_out, ctx->d_rgba.p, px * 4));
+    if (depth_out) CU(d2h(ctx, depth_out, ctx->d_depth_img.p, px * 4));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return PRV_OK;
+}
+
+int prv_timing_reset(prv_ctx* ctx) {
+    if (!ctx) return PRV_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (auto& s : ctx->spans) {
+        ctx->free_events.push_back(s.a);
+        ctx->free_events.push_back(s.b);
+    }
+    ctx->spans.clear();
+    return PRV_OK;
+}
+
+int prv_get_timing(prv_ctx* ctx, prv_timing* out) {
+    if (!ctx || !out) return PRV_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms[K_NCLASS] = {0};
+    uint32_t cnt[K_NCLASS] = {0};
+    for (auto& s : ctx->spans) {
+        float t = 0.0f;
+        CU(cudaEventElapsedTime(&t, s.a, s.b));
+        ms[s.cls] += t;
+        cnt[s.cls] += s.launches;
+    }
+    out->cast_ms = ms[K_CAST];       out->cast_launches = cnt[K_CAST];
+    out->project_ms = ms[K_PROJECT]; out->project_launches = cnt[K_PROJECT];
+    out->count_ms = ms[K_COUNT];     out->count_launches = cnt[K_COUNT];
+    out->greedy_ms = ms[K_GREEDY];   out->greedy_launches = cnt[K_GREEDY];
+    out->splat_ms = ms[K_SPLAT];     out->splat_launches = cnt[K_SPLAT];
+    out->resolve_ms = ms[K_RESOLVE]; out->resolve_launches = cnt[K_RESOLVE];
+    out->other_ms = ms[K_OTHER];     out->other_launches = cnt[K_OTHER];
+    return PRV_OK;
+}
+
+int prv_event_record(prv_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 16) return PRV_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(ctx->slots[slot], ctx->stream));
+    return PRV_OK;
+}
+
+int prv_event_elapsed_ms(prv_ctx* ctx, int a, int b, float* ms_out) {
+    if (!ctx || !ms_out || a < 0 || a >= 16 || b < 0 || b >= 16) return PRV_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventSynchronize(ctx->slots[b]));
+    CU(cudaEventElapsedTime(ms_out, ctx->slots[a], ctx->slots[b]));
+    return PRV_OK;
+}
+
+int prv_reset_counters(prv_ctx* ctx) {
+    if (!ctx) return PRV_ERR_INVALID;
+    ctx->n_launches = ctx->h2d_bytes = ctx->d2h_bytes = 0;
+    return PRV_OK;
+}
+
+int prv_get_counters(prv_ctx* ctx, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+    if (!ctx) return PRV_ERR_INVALID;
+    if (kernel_launches) *kernel_launches = ctx->n_launches;
+    if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
+    return PRV_OK;
+}
+
+int prv_map_bytes(prv_ctx* ctx, uint64_t* bitmap_bytes) {
+    if (!ctx || !ctx->have_map || !bitmap_bytes) return PRV_ERR_INVALID;
+    *bitmap_bytes = (uint64_t)ctx->map.wx * ctx->map.n[1] * ctx->map.n[2] * 4;
+    return PRV_OK;
+}
+
+int prv_flush_l2(prv_ctx* ctx) {
+    if (!ctx) return PRV_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)256 << 20;  // > 126 MB L2
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_flush, bytes))) return rc;
+    CU(cudaMemsetAsync(ctx->d_flush.p, 0x5A, bytes, ctx->stream));
+    return PRV_OK;
+}
+
+// ---------------------------------------------------------------- NCCL (dlopen)
+static int load_nccl(prv_ctx* ctx, NcclApi& api) {
+    if (api.handle) return PRV_OK;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nme : names) {
+        api.handle = dlopen(nme, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) return fail(ctx, PRV_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    api.GetUniqueId = (int (*)(void*))dlsym(api.handle, "ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(api.handle, "ncclCommInitRank");
+    api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(api.handle, "ncclAllGather");
+    api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
+    api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllGather || !api.CommDestroy) return fail(ctx, PRV_ERR_NCCL, "libnccl is missing required symbols");
+    return PRV_OK;
+}
+
+int prv_comm_unique_id(void* id_out_128) {
+    if (!id_out_128) return PRV_ERR_INVALID;
+    NcclApi api;
+    int rc = load_nccl(nullptr, api);
+    if (rc) return rc;
+    const int r = api.GetUniqueId(id_out_128);
+    return r == 0 ? PRV_OK : fail(nullptr, PRV_ERR_NCCL, "ncclGetUniqueId failed: %d", r);
+}
+
+int prv_comm_init(prv_ctx* ctx, const void* id_128, int rank, int nranks) {
+    if (!ctx || !id_128 || nranks < 1 || rank < 0 || rank >= nranks) return PRV_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    int rc = load_nccl(ctx, ctx->nccl);
+    if (rc) return rc;
+    Id128 id;
+    std::memcpy(id.b, id_128, 128);
+    const int r = ctx->nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (r != 0) return fail(ctx, PRV_ERR_NCCL, "ncclCommInitRank failed: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(r) : "?");
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return PRV_OK;
+}
+
+int prv_allgather_bitsets_async(prv_ctx* ctx) {
+    if (!ctx) return PRV_ERR_INVALID;
+    if (!ctx->cast_done) return fail(ctx, PRV_ERR_INVALID, "prv_allgather_bitsets: nothing cast yet");
+    if (!ctx->comm) return fail(ctx, PRV_ERR_INVALID, "prv_allgather_bitsets: prv_comm_init has not been called");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t V = ctx->V, words = ctx->map.words64, G = (uint32_t)ctx->nranks;
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_all_rows, (size_t)G * V * words * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->d_all_ids, (size_t)G * V * 4))) return rc;
+    {
+        Span s(ctx, K_OTHER, 2);
+        int r = ctx->nccl.AllGather(ctx->d_bitsets.p, ctx->d_all_rows.p, (size_t)V * words, /*ncclUint64*/ 5, ctx->comm, ctx->stream);
+        if (r == 0) r = ctx->nccl.AllGather(ctx->d_view_ids.p, ctx->d_all_ids.p, (size_t)V, /*ncclUint32*/ 3, ctx->comm, ctx->stream);
+        if (r != 0) return fail(ctx, PRV_ERR_NCCL, "ncclAllGather failed: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(r) : "?");
+    }
+    // row_of_id for the gathered table (ids are a permutation of 0..G*V-1 by contract)
+    std::vector<uint32_t> ids((size_t)G * V);
+    CU(d2h(ctx, ids.data(), ctx->d_all_ids.p, ids.size() * 4));
+    CU(cudaStreamSynchronize(ctx->stream));
+    uint32_t max_id = 0;
+    for (uint32_t id : ids) max_id = std::max(max_id, id);
+    std::vector<uint32_t>& row_of_id = ctx->h_row_of_id;
+    row_of_id.assign((size_t)max_id + 1, kNone);
+    for (size_t r = 0; r < ids.size(); r++) row_of_id[ids[r]] = (uint32_t)r;
+    if ((rc = ensure(ctx, ctx->d_row_of_id, 4 * row_of_id.size()))) return rc;
+    CU(h2d(ctx, ctx->d_row_of_id.p, row_of_id.data(), 4 * row_of_id.size()));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->id_space = max_id + 1;
+    ctx->gathered = true;
+    ctx->g_rows = ptr<uint64_t>(ctx->d_all_rows);
+    ctx->g_nrows = G * V;
+    return PRV_OK;
+}
+
+int prv_comm_destroy(prv_ctx* ctx) {
+    if (!ctx) return PRV_ERR_INVALID;
+    if (ctx->comm && ctx->nccl.CommDestroy) {
+        ctx->nccl.CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
+    return PRV_OK;
+}
+
+}  // extern "C"

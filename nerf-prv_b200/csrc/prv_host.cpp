@@ -1,0 +1,139 @@
+// prv_host.cpp -- the pure-host entry points of include/prv.h (prv_host_*): pose, view-space,
+// cloud normalisation and ground-truth map insertion arithmetic of the reference, implemented once
+// on top of the host mirror classes so C++ and ctypes callers share one implementation.
+// Compile with -ffp-contract=off.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <utility>
+#include <vector>
+
+#include "../../include/prv.h"
+#include "../host/View_Space.hpp"
+#include "prv_keys.hpp"
+
+using prv::Matrix4d;
+using prv::Vector3d;
+
+extern "C" {
+
+int prv_abi_version(void) { return PRV_ABI_VERSION; }
+
+int prv_host_mat4_inverse(const double m[16], double out[16]) {
+    if (!m || !out) return PRV_ERR_INVALID;
+    Matrix4d::FromRowMajor(m).inverse().toRowMajor(out);
+    return PRV_OK;
+}
+
+int prv_host_view_pose(const double now_camera_pose_world[16], const double init_pos[3], const double object_center_world[3],
+                       double pose_out[16]) {
+    if (!now_camera_pose_world || !init_pos || !object_center_world || !pose_out) return PRV_ERR_INVALID;
+    View v(Vector3d(init_pos[0], init_pos[1], init_pos[2]));
+    v.get_next_camera_pos(Matrix4d::FromRowMajor(now_camera_pose_world),
+                          Vector3d(object_center_world[0], object_center_world[1], object_center_world[2]), 0);
+    v.pose.toRowMajor(pose_out);
+    return PRV_OK;
+}
+
+int prv_host_view_pose_world(const double now_camera_pose_world[16], const double pose[16], double out[16]) {
+    if (!now_camera_pose_world || !pose || !out) return PRV_ERR_INVALID;
+    (Matrix4d::FromRowMajor(now_camera_pose_world) * Matrix4d::FromRowMajor(pose).inverse()).toRowMajor(out);
+    return PRV_OK;
+}
+
+int prv_host_view_space(const float* pts, uint64_t P, const double* pt_sphere, int N, double pt_norm, double view_space_radius,
+                        double center_out[3], double* predicted_size_out, double* init_pos_out, int* n_views_out) {
+    if (!pts || !pt_sphere || P == 0 || N < 0 || !center_out || !predicted_size_out || !init_pos_out || !n_views_out)
+        return PRV_ERR_INVALID;
+    // View_Space.hpp:533-547 of the reference; float cloud coordinates widened to double (:567-569)
+    double c[3] = {0.0, 0.0, 0.0};
+    for (uint64_t i = 0; i < P; i++)
+        for (int a = 0; a < 3; a++) c[a] += (double)pts[3 * i + a];
+    for (int a = 0; a < 3; a++) c[a] /= (double)P;
+    const Vector3d center(c[0], c[1], c[2]);
+    double size = 0.0;
+    for (uint64_t i = 0; i < P; i++)
+        size = std::max(size, (center - Vector3d(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2])).norm());
+    size *= 17.0 / 16.0;
+    int nv = 0;
+    for (int i = 0; i < N; i++) {
+        const double* s = pt_sphere + 3 * (size_t)i;
+        if (s[2] < 0) continue;  // :549
+        const double scale = 1.0 / pt_norm * view_space_radius;
+        for (int a = 0; a < 3; a++) init_pos_out[3 * nv + a] = s[a] * scale + c[a];
+        nv++;
+    }
+    for (int a = 0; a < 3; a++) center_out[a] = c[a];
+    *predicted_size_out = size;
+    *n_views_out = nv;
+    return PRV_OK;
+}
+
+int prv_host_normalize_cloud(float* pts, uint64_t P, double target_size, double* predicted_size_before_out) {
+    if (!pts || P == 0 || !(target_size > 0)) return PRV_ERR_INVALID;
+    // main.cpp:674: get_toward_pose(4) maps (x,y,z) -> (x,z,y); the 0/1 products are exact, so it is a swap
+    for (uint64_t i = 0; i < P; i++) std::swap(pts[3 * i + 1], pts[3 * i + 2]);
+    auto centroid = [&](double c[3]) {
+        c[0] = c[1] = c[2] = 0.0;
+        for (uint64_t i = 0; i < P; i++)
+            for (int a = 0; a < 3; a++) c[a] += (double)pts[3 * i + a];
+        for (int a = 0; a < 3; a++) c[a] /= (double)P;
+    };
+    double c[3];
+    centroid(c);  // main.cpp:768-783
+    for (uint64_t i = 0; i < P; i++)
+        for (int a = 0; a < 3; a++) pts[3 * i + a] = (float)((double)pts[3 * i + a] - c[a]);  // :786-790
+    centroid(c);  // :811-821
+    const Vector3d center(c[0], c[1], c[2]);
+    double size = 0.0;  // :828-832
+    for (uint64_t i = 0; i < P; i++)
+        size = std::max(size, (center - Vector3d(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2])).norm());
+    size *= 17.0 / 16.0;
+    if (predicted_size_before_out) *predicted_size_before_out = size;
+    const double scale = target_size / size;  // :962 (random_size / predicted_size)
+    const float unit = 1.0f;                  // :756
+    for (uint64_t i = 0; i < P; i++)
+        for (int a = 0; a < 3; a++) pts[3 * i + a] = (float)((double)pts[3 * i + a] * scale * unit);  // :1008-1010
+    return PRV_OK;
+}
+
+int prv_host_build_map(const float* pts, const uint8_t* rgb, uint64_t P, double resolution, uint16_t* keys_out,
+                       uint8_t* rgb_out, uint32_t* n_out) {
+    if (!pts || !keys_out || !n_out || !(resolution > 0)) return PRV_ERR_INVALID;
+    const double rf = 1.0 / resolution;
+    // (morton, point index): sorting groups points of one voxel with the first-inserted point first,
+    // which is the voxel whose colour the reference keeps (main.cpp:1015-1021).
+    std::vector<std::pair<uint64_t, uint64_t>> order;
+    order.reserve(P);
+    for (uint64_t i = 0; i < P; i++) {
+        uint16_t k[3];
+        if (!prv::coord_to_key_checked(pts[3 * i], rf, k[0]) || !prv::coord_to_key_checked(pts[3 * i + 1], rf, k[1]) ||
+            !prv::coord_to_key_checked(pts[3 * i + 2], rf, k[2]))
+            continue;
+        order.emplace_back(prv::morton_code(k[0], k[1], k[2]), i);
+    }
+    std::sort(order.begin(), order.end());
+    uint32_t n = 0;
+    uint64_t prev = ~0ull;
+    for (const auto& e : order) {
+        if (e.first == prev) continue;
+        prev = e.first;
+        uint16_t k[3];
+        prv::morton_decode(e.first, k);
+        for (int a = 0; a < 3; a++) keys_out[3 * (size_t)n + a] = k[a];
+        if (rgb_out)
+            for (int a = 0; a < 3; a++) rgb_out[3 * (size_t)n + a] = rgb ? rgb[3 * e.second + a] : (uint8_t)0;
+        n++;
+    }
+    *n_out = n;
+    return PRV_OK;
+}
+
+float prv_splat_focal(const prv_intrinsics* intr) {
+    if (!intr) return 0.0f;
+    // PCL 1.9.1 PCLVisualizer::setCameraParameters(intrinsics, extrinsics) (call: reference main.cpp:79):
+    // fovy = 2*atan(window_h / (2 fy)) with window_h = 2*(int)cy; the window is then forced to W x H (:80-84).
+    return (float)((double)intr->height * (double)intr->fy / (2.0 * (double)(int)intr->ppy));
+}
+
+}  // extern "C"
