@@ -81,11 +81,14 @@ typedef struct prv_cast_stats {
     uint64_t probes_in;  /* DDA steps whose key lies inside the occupancy AABB     */
     uint64_t hits;       /* rays with a first-hit voxel                            */
     uint64_t steps;      /* DDA steps actually executed by the chosen variant      */
+    uint64_t marched;    /* rays that survived the conservative culls and were marched */
 } prv_cast_stats;
 
 /* per-kernel-class device time accumulated with CUDA events on the ctx stream since prv_timing_reset */
 typedef struct prv_timing {
-    float    cast_ms;     uint32_t cast_launches;
+    float    cast_ms;     uint32_t cast_launches;    /* single-kernel PLAIN/FAST cast, or cull+march together */
+    float    cull_ms;     uint32_t cull_launches;    /* AXIS pipeline, kernel 1 */
+    float    march_ms;    uint32_t march_launches;   /* AXIS pipeline, kernel 2 (the dominant kernel) */
     float    project_ms;  uint32_t project_launches;
     float    count_ms;    uint32_t count_launches;
     float    greedy_ms;   uint32_t greedy_launches;

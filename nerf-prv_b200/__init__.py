@@ -36,14 +36,15 @@ class Intrinsics(C.Structure):
 
 
 class CastStats(C.Structure):
-    _fields_ = [("rays", C.c_uint64), ("probes_in", C.c_uint64), ("hits", C.c_uint64), ("steps", C.c_uint64)]
+    _fields_ = [("rays", C.c_uint64), ("probes_in", C.c_uint64), ("hits", C.c_uint64), ("steps", C.c_uint64), ("marched", C.c_uint64)]
 
     def as_dict(self):
-        return {"rays": self.rays, "probes_in": self.probes_in, "hits": self.hits, "steps": self.steps}
+        return {"rays": self.rays, "probes_in": self.probes_in, "hits": self.hits, "steps": self.steps, "marched": self.marched}
 
 
 class Timing(C.Structure):
-    _fields_ = [("cast_ms", C.c_float), ("cast_launches", C.c_uint32), ("project_ms", C.c_float), ("project_launches", C.c_uint32),
+    _fields_ = [("cast_ms", C.c_float), ("cast_launches", C.c_uint32), ("cull_ms", C.c_float), ("cull_launches", C.c_uint32),
+                ("march_ms", C.c_float), ("march_launches", C.c_uint32), ("project_ms", C.c_float), ("project_launches", C.c_uint32),
                 ("count_ms", C.c_float), ("count_launches", C.c_uint32), ("greedy_ms", C.c_float), ("greedy_launches", C.c_uint32),
                 ("splat_ms", C.c_float), ("splat_launches", C.c_uint32), ("resolve_ms", C.c_float), ("resolve_launches", C.c_uint32),
                 ("other_ms", C.c_float), ("other_launches", C.c_uint32)]

@@ -22,58 +22,40 @@ using namespace prvk;
 // kernels
 // =====================================================================================================
 
-// One thread per pixel of a 32x8 tile (each warp an 8x4 patch, so the lanes of a warp march similar
-// step counts).  blockIdx.x = tile, blockIdx.y = view.
-template <int VARIANT, bool MASKED>
-__global__ void __launch_bounds__(256) raycast_kernel(const CastParams p) {
-    __shared__ ViewConst s_vc;
-    const uint32_t view = blockIdx.y + p.view_base;
-    {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.views + view);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_vc);
-        for (int i = threadIdx.x; i < (int)(sizeof(ViewConst) / 4); i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    const ViewConst& vc = s_vc;
-
-    const int tiles_x = (p.GW + 31) >> 5;
-    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+// deterministic counters, one set per view: block-reduce, then one atomic per counter per block (per-warp atomics on
+// one address serialise in L2 and were measured to bound the whole kernel)
+__device__ __forceinline__ void commit_stats(unsigned long long* view_stats, uint32_t rays, uint32_t probes, uint32_t hits, uint32_t steps) {
+    __shared__ uint32_t s_cnt[4][8];
+    uint32_t c[4] = {rays, probes, hits, steps};
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        for (int o = 16; o > 0; o >>= 1) c[i] += __shfl_down_sync(0xFFFFFFFFu, c[i], o);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int px = (tile_x << 5) + ((warp & 3) << 3) + (lane & 7);
-    const int py = (tile_y << 3) + ((warp >> 2) << 2) + (lane >> 3);
-    const bool in_grid = px < p.GW && py < p.GH;
-    const unsigned long long pid = (unsigned long long)py * p.GW + px;
-
-    bool active = in_grid && (vc.flags & kViewInMap) && !(vc.flags & kViewInObject);
-    if (MASKED && active) {
-        const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
-        active = (w >> (pid & 31)) & 1u;
+    if (lane == 0)
+        for (int i = 0; i < 4; i++) s_cnt[i][warp] = c[i];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        unsigned long long t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_cnt[threadIdx.x][w];
+        if (t) atomicAdd(view_stats + threadIdx.x, t);
     }
+}
 
-    CastResult res;
-    res.rank = kNone;
-    res.steps = 0;
-    res.probes = 0;
-    res.k0 = res.k1 = res.k2 = 0;
-    if (active) {
-        RayState r;
-        if (setup_ray(p.cam, vc, p.map.resolution, px, py, r)) {
-            if (VARIANT == PRV_VARIANT_PLAIN || !(vc.flags & kViewFastOk))
-                march_plain(p.map, p.cam, vc, r, res);
-            else if (VARIANT == PRV_VARIANT_FAST)
-                march_fast(p.map, vc, r, res);
-            else
-                march_axis(p.map, vc, r, res);
-        }
-    }
+__device__ __forceinline__ void load_view_const(ViewConst& dst, const ViewConst* src) {
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(&dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(ViewConst) / 4); i += blockDim.x) d32[i] = s32[i];
+    __syncthreads();
+}
 
+__device__ __forceinline__ void write_hit(const CastParams& p, const ViewConst& vc, uint32_t view, unsigned long long pid, const CastResult& res) {
     if (res.rank != kNone) {
         uint32_t* row = p.bitsets32 + (size_t)view * (2u * p.map.words64);
         const uint32_t bit = 1u << (res.rank & 31);
         uint32_t* w = row + (res.rank >> 5);
         if (!(*reinterpret_cast<volatile uint32_t*>(w) & bit)) atomicOr(w, bit);
     }
-    if (in_grid && p.pix_hit && (!MASKED || active)) {
+    if (p.pix_hit) {
         p.pix_hit[(size_t)view * p.pix_stride + pid] = res.rank;
         if (p.pix_depth) {
             float d = 0.0f;
@@ -81,21 +63,138 @@ __global__ void __launch_bounds__(256) raycast_kernel(const CastParams p) {
             p.pix_depth[(size_t)view * p.pix_stride + pid] = d;
         }
     }
+}
 
-    // deterministic counters: warp-reduce then one atomic per warp
-    unsigned long long c_rays = active ? 1ull : 0ull, c_probes = res.probes, c_hits = res.rank != kNone ? 1ull : 0ull, c_steps = res.steps;
-    for (int o = 16; o > 0; o >>= 1) {
-        c_rays += __shfl_down_sync(0xFFFFFFFFu, c_rays, o);
-        c_probes += __shfl_down_sync(0xFFFFFFFFu, c_probes, o);
-        c_hits += __shfl_down_sync(0xFFFFFFFFu, c_hits, o);
-        c_steps += __shfl_down_sync(0xFFFFFFFFu, c_steps, o);
+// ---- AXIS pipeline, kernel 1: loose float cull of every pixel, survivors compacted into a per-view queue ----------
+// 32x8 pixel tile per block (each warp an 8x4 patch); culled pixels get their "no hit" outputs here, survivors are
+// marched by march_kernel.  blockIdx.x = tile, blockIdx.y = view.
+template <bool MASKED>
+__global__ void __launch_bounds__(256) cull_kernel(const CastParams p) {
+    __shared__ ViewConst s_vc;
+    __shared__ uint32_t s_woff[8];
+    __shared__ uint32_t s_base;
+    const uint32_t view = blockIdx.y + p.view_base;
+    load_view_const(s_vc, p.views + view);
+    const ViewConst& vc = s_vc;
+    const int tiles_x = (p.GW + 31) >> 5;
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = (tile_x << 5) + ((warp & 3) << 3) + (lane & 7);
+    const int py = (tile_y << 3) + ((warp >> 2) << 2) + (lane >> 3);
+    const bool in_grid = px < p.GW && py < p.GH;
+    const unsigned long long pid = (unsigned long long)py * p.GW + px;
+    bool active = in_grid && (vc.flags & kViewInMap) && !(vc.flags & kViewInObject);
+    if (MASKED && active) {
+        const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
+        active = (w >> (pid & 31)) & 1u;
     }
-    if (lane == 0 && c_rays) {
-        atomicAdd(p.stats + 0, c_rays);
-        atomicAdd(p.stats + 1, c_probes);
-        atomicAdd(p.stats + 2, c_hits);
-        atomicAdd(p.stats + 3, c_steps);
+    bool survive = false;
+    if (active) {
+        if (!(vc.flags & kViewFastOk)) {
+            survive = true;  // this view needs the literal march (max-range test): no cull
+        } else {
+            float dx, dy, dz;
+            ray_direction(p.cam, vc, px, py, dx, dy, dz);
+            survive = !loose_miss(p.map, vc, dx, dy, dz);
+        }
     }
+    if (in_grid && !survive && p.pix_hit && (!MASKED || active)) {
+        p.pix_hit[(size_t)view * p.pix_stride + pid] = kNone;
+        if (p.pix_depth) p.pix_depth[(size_t)view * p.pix_stride + pid] = 0.0f;
+    }
+    // block-level compaction: one atomic per block on the view's counter
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, survive);
+    const uint32_t act = __ballot_sync(0xFFFFFFFFu, active);
+    if (lane == 0) s_woff[warp] = __popc(bal) | (__popc(act) << 16);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0, rays = 0;
+        for (int w = 0; w < 8; w++) {
+            const uint32_t c = s_woff[w] & 0xFFFFu;
+            rays += s_woff[w] >> 16;
+            s_woff[w] = tot;
+            tot += c;
+        }
+        s_base = tot ? atomicAdd(p.qcount + view, tot) : 0u;
+        if (rays) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)rays);
+    }
+    __syncthreads();
+    if (survive) p.queue[(size_t)view * p.queue_cap + s_base + s_woff[warp] + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)pid;
+}
+
+// ---- AXIS pipeline, kernel 2: dense warps of surviving rays; gridDim.x persistent blocks per view ------------------
+__global__ void __launch_bounds__(256) march_kernel(const CastParams p) {
+    __shared__ ViewConst s_vc;
+    const uint32_t view = blockIdx.y + p.view_base;
+    const uint32_t count = p.qcount[view];
+    if ((unsigned long long)blockIdx.x * 256ull >= count) return;
+    load_view_const(s_vc, p.views + view);
+    const ViewConst& vc = s_vc;
+    const bool plain = !(vc.flags & kViewFastOk);
+    uint32_t c_probes = 0, c_hits = 0, c_steps = 0;
+    for (unsigned long long base = (unsigned long long)blockIdx.x * 256ull; base < count; base += (unsigned long long)gridDim.x * 256ull) {
+        const unsigned long long idx = base + threadIdx.x;
+        if (idx >= count) continue;
+        const uint32_t pid = p.queue[(size_t)view * p.queue_cap + idx];
+        const int py = (int)(pid / (uint32_t)p.GW), px = (int)(pid - (uint32_t)py * (uint32_t)p.GW);
+        CastResult res;
+        res.rank = kNone;
+        res.steps = 0;
+        res.probes = 0;
+        res.k0 = res.k1 = res.k2 = 0;
+        RayState r;
+        float dx, dy, dz;
+        ray_direction(p.cam, vc, px, py, dx, dy, dz);
+        if (ray_init(vc, p.map.resolution, dx, dy, dz, r)) {
+            if (plain)
+                march_plain(p.map, p.cam, vc, r, res);
+            else
+                march_axis(p.map, vc, r, res);
+        }
+        write_hit(p, vc, view, pid, res);
+        c_probes += res.probes;
+        c_hits += res.rank != kNone ? 1u : 0u;
+        c_steps += res.steps;
+    }
+    commit_stats(p.stats + 4 * (size_t)view, 0u, c_probes, c_hits, c_steps);
+}
+
+// ---- PLAIN / FAST variants: one kernel, one thread per pixel of a 32x8 tile ----------------------------------------
+template <int VARIANT, bool MASKED>
+__global__ void __launch_bounds__(256) raycast_kernel(const CastParams p) {
+    __shared__ ViewConst s_vc;
+    const uint32_t view = blockIdx.y + p.view_base;
+    load_view_const(s_vc, p.views + view);
+    const ViewConst& vc = s_vc;
+    const int tiles_x = (p.GW + 31) >> 5;
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = (tile_x << 5) + ((warp & 3) << 3) + (lane & 7);
+    const int py = (tile_y << 3) + ((warp >> 2) << 2) + (lane >> 3);
+    const bool in_grid = px < p.GW && py < p.GH;
+    const unsigned long long pid = (unsigned long long)py * p.GW + px;
+    bool active = in_grid && (vc.flags & kViewInMap) && !(vc.flags & kViewInObject);
+    if (MASKED && active) {
+        const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
+        active = (w >> (pid & 31)) & 1u;
+    }
+    CastResult res;
+    res.rank = kNone;
+    res.steps = 0;
+    res.probes = 0;
+    res.k0 = res.k1 = res.k2 = 0;
+    if (active) {
+        RayState r;
+        const bool plain = VARIANT == PRV_VARIANT_PLAIN || !(vc.flags & kViewFastOk);
+        if (setup_ray(p.cam, vc, p.map.resolution, px, py, r)) {
+            if (plain)
+                march_plain(p.map, p.cam, vc, r, res);
+            else
+                march_fast(p.map, vc, r, res);
+        }
+    }
+    if (in_grid && (!MASKED || active)) write_hit(p, vc, view, pid, res);
+    commit_stats(p.stats + 4 * (size_t)view, active ? 1u : 0u, res.probes, res.rank != kNone ? 1u : 0u, res.steps);
 }
 
 // voxel-driven mode, stage 1 (main.cpp:243-251 of the reference): project every occupied voxel centre, mark its
@@ -299,7 +398,7 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-enum KClass { K_CAST = 0, K_PROJECT, K_COUNT, K_GREEDY, K_SPLAT, K_RESOLVE, K_OTHER, K_NCLASS };
+enum KClass { K_CAST = 0, K_CULL, K_MARCH, K_PROJECT, K_COUNT, K_GREEDY, K_SPLAT, K_RESOLVE, K_OTHER, K_NCLASS };
 
 struct TimedSpan {
     int cls;
@@ -336,7 +435,7 @@ struct prv_ctx {
     DevMap map{};
     double resolution = 0;
     int lo[3] = {0, 0, 0}, n[3] = {0, 0, 0};
-    DevBuf d_bitmap, d_prefix, d_leaf_of_raster, d_keys, d_rgb;
+    DevBuf d_bitmap, d_bitmap_pad, d_prefix, d_leaf_of_raster, d_keys, d_rgb;
     std::vector<uint16_t> h_keys;
 
     // camera
@@ -353,6 +452,7 @@ struct prv_ctx {
     uint32_t id_space = 0;
 
     // cast outputs
+    DevBuf d_queue, d_qcount;
     DevBuf d_bitsets, d_counts, d_stats, d_pix_hit, d_pix_depth, d_mask, d_voxel_pix, d_voxel_hit, d_points;
     int last_mode = -1;
     bool have_pixels = false;
@@ -609,9 +709,9 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
     int rc;
     if ((rc = ensure(ctx, ctx->d_bitsets, (size_t)V * words * 8))) return rc;
     if ((rc = ensure(ctx, ctx->d_counts, (size_t)V * 4))) return rc;
-    if ((rc = ensure(ctx, ctx->d_stats, 4 * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->d_stats, (size_t)V * 4 * 8))) return rc;
     CU(cudaMemsetAsync(ctx->d_bitsets.p, 0, (size_t)V * words * 8, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_stats.p, 0, 4 * 8, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_stats.p, 0, (size_t)V * 4 * 8, ctx->stream));
 
     CastParams p{};
     p.map = ctx->map;
@@ -641,6 +741,14 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
         CU(cudaMemsetAsync(ctx->d_mask.p, 0, (size_t)V * ctx->mask_words * 4, ctx->stream));
         p.mask = ptr<uint32_t>(ctx->d_mask);
     }
+    if (ctx->variant == PRV_VARIANT_AXIS) {
+        if ((rc = ensure(ctx, ctx->d_queue, (size_t)V * ctx->pix_stride * 4))) return rc;
+        if ((rc = ensure(ctx, ctx->d_qcount, (size_t)V * 4))) return rc;
+        CU(cudaMemsetAsync(ctx->d_qcount.p, 0, (size_t)V * 4, ctx->stream));
+        p.queue = ptr<uint32_t>(ctx->d_queue);
+        p.qcount = ptr<uint32_t>(ctx->d_qcount);
+        p.queue_cap = ctx->pix_stride;
+    }
     const uint32_t tiles = (uint32_t)(((p.GW + 31) / 32) * ((p.GH + 7) / 8));
     for (uint32_t vb = 0; vb < V; vb += 32768) {
         const uint32_t vn = std::min<uint32_t>(32768, V - vb);
@@ -650,15 +758,28 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
                 ctx->map, ctx->cam, ptr<ViewConst>(ctx->d_views), vb, ptr<uint32_t>(ctx->d_mask), ctx->mask_words, ptr<uint32_t>(ctx->d_voxel_pix));
         }
         p.view_base = vb;
-        {
+        if (ctx->variant == PRV_VARIANT_AXIS) {
+            // cull + compact, then march the survivors in dense warps
+            const dim3 grid(tiles, vn);
+            {
+                Span s(ctx, K_CULL, 1);
+                if (voxel)
+                    cull_kernel<true><<<grid, 256, 0, ctx->stream>>>(p);
+                else
+                    cull_kernel<false><<<grid, 256, 0, ctx->stream>>>(p);
+            }
+            Span s(ctx, K_MARCH, 1);
+            const uint32_t max_chunks = (uint32_t)((ctx->pix_stride + 255) / 256);
+            uint32_t per_view = (uint32_t)((ctx->sm_count * 16 + vn - 1) / vn);
+            per_view = std::max(1u, std::min(per_view, max_chunks));
+            march_kernel<<<dim3(per_view, vn), 256, 0, ctx->stream>>>(p);
+        } else {
             Span s(ctx, K_CAST, 1);
             const dim3 grid(tiles, vn);
             if (ctx->variant == PRV_VARIANT_PLAIN)
                 launch_cast<PRV_VARIANT_PLAIN>(ctx, p, voxel, grid);
-            else if (ctx->variant == PRV_VARIANT_FAST)
-                launch_cast<PRV_VARIANT_FAST>(ctx, p, voxel, grid);
             else
-                launch_cast<PRV_VARIANT_AXIS>(ctx, p, voxel, grid);
+                launch_cast<PRV_VARIANT_FAST>(ctx, p, voxel, grid);
         }
     }
     {
@@ -784,8 +905,8 @@ void prv_destroy(prv_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     prv_comm_destroy(ctx);
-    DevBuf* bufs[] = {&ctx->d_bitmap, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
-                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
+    DevBuf* bufs[] = {&ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
+                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
                       &ctx->d_voxel_pix, &ctx->d_voxel_hit, &ctx->d_points, &ctx->d_best, &ctx->d_cov[0], &ctx->d_cov[1], &ctx->d_all_rows,
                       &ctx->d_all_ids, &ctx->d_cloud_xyz, &ctx->d_cloud_rgb, &ctx->d_corner, &ctx->d_rgba, &ctx->d_depth_img, &ctx->d_flush};
     for (DevBuf* b : bufs) release(*b);
@@ -856,7 +977,33 @@ int prv_set_map(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, uint32_t
         const uint32_t bit = (keys[3 * i] - lo[0]) & 31;
         leaf_of_raster[prefix[w] + (uint32_t)__builtin_popcount(bitmap[w] & ((1u << bit) - 1u))] = i;
     }
+    // shell-padded bitmap for the branch-free in-AABB march
+    int row_log2 = 5;
+    while ((1 << row_log2) < n[0] + 2) row_log2++;
+    const size_t pad_rows = (size_t)(n[1] + 2) * (n[2] + 2);
+    // slack of 3 planes (+1 row) on both sides: the 4-deep speculative march may step up to 3 cells past the shell
+    const size_t slack_bits = ((size_t)3 * (n[1] + 2) + 2) << row_log2;
+    const size_t pad_words = ((pad_rows << row_log2) + 2 * slack_bits) / 32;
+    if ((pad_rows << row_log2) + 2 * slack_bits >= ((size_t)1 << 31)) return fail(ctx, PRV_ERR_UNSUPPORTED, "prv_set_map: occupancy AABB too large for the padded bitmap");
+    std::vector<uint32_t> pad(pad_words, 0u);
+    auto pad_set = [&](int c0, int c1, int c2) {  // padded coordinates
+        const size_t L = slack_bits + ((((size_t)c2 * (n[1] + 2)) + (size_t)c1) << row_log2) + (size_t)c0;
+        pad[L >> 5] |= 1u << (L & 31);
+    };
+    for (int c2 = 0; c2 < n[2] + 2; c2++)
+        for (int c1 = 0; c1 < n[1] + 2; c1++) {
+            const bool shell_row = c2 == 0 || c2 == n[2] + 1 || c1 == 0 || c1 == n[1] + 1;
+            if (shell_row) {
+                for (int c0 = 0; c0 < n[0] + 2; c0++) pad_set(c0, c1, c2);
+            } else {
+                pad_set(0, c1, c2);
+                pad_set(n[0] + 1, c1, c2);
+            }
+        }
+    for (uint32_t i = 0; i < N; i++) pad_set(keys[3 * i] - lo[0] + 1, keys[3 * i + 1] - lo[1] + 1, keys[3 * i + 2] - lo[2] + 1);
     int rc;
+    if ((rc = ensure(ctx, ctx->d_bitmap_pad, pad_words * 4))) return rc;
+    CU(h2d(ctx, ctx->d_bitmap_pad.p, pad.data(), pad_words * 4));
     if ((rc = ensure(ctx, ctx->d_bitmap, nwords * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_prefix, nwords * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_leaf_of_raster, (size_t)N * 4))) return rc;
@@ -884,6 +1031,13 @@ int prv_set_map(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, uint32_t
     ctx->map.n_occ = N;
     ctx->map.words64 = words_for(N);
     ctx->map.bitmap = ptr<uint32_t>(ctx->d_bitmap);
+    ctx->map.bitmap_pad = ptr<uint32_t>(ctx->d_bitmap_pad);
+    ctx->map.pad_row_log2 = row_log2;
+    ctx->map.pad_bit_offset = (uint32_t)slack_bits;
+    for (int a = 0; a < 3; a++) {
+        ctx->map.bmin[a] = (float)((double)(lo[a] - 2 - prv::kTreeMaxVal) * resolution);
+        ctx->map.bmax[a] = (float)((double)(lo[a] + n[a] + 2 - prv::kTreeMaxVal) * resolution);
+    }
     ctx->map.prefix = ptr<uint32_t>(ctx->d_prefix);
     ctx->map.leaf_of_raster = ptr<uint32_t>(ctx->d_leaf_of_raster);
     ctx->map.keys = ptr<uint16_t>(ctx->d_keys);
@@ -1035,13 +1189,22 @@ int prv_get_cast_stats(prv_ctx* ctx, prv_cast_stats* out) {
     if (!ctx || !out) return PRV_ERR_INVALID;
     if (!ctx->cast_done) return fail(ctx, PRV_ERR_INVALID, "prv_get_cast_stats: nothing cast yet");
     CU(cudaSetDevice(ctx->device));
-    unsigned long long s[4];
-    CU(d2h(ctx, s, ctx->d_stats.p, sizeof(s)));
+    std::vector<unsigned long long> s((size_t)ctx->V * 4);
+    CU(d2h(ctx, s.data(), ctx->d_stats.p, s.size() * 8));
     CU(cudaStreamSynchronize(ctx->stream));
-    out->rays = s[0];
-    out->probes_in = s[1];
-    out->hits = s[2];
-    out->steps = s[3];
+    out->rays = out->probes_in = out->hits = out->steps = out->marched = 0;
+    if (ctx->variant == PRV_VARIANT_AXIS) {
+        std::vector<uint32_t> q(ctx->V);
+        CU(d2h(ctx, q.data(), ctx->d_qcount.p, q.size() * 4));
+        CU(cudaStreamSynchronize(ctx->stream));
+        for (uint32_t c : q) out->marched += c;
+    }
+    for (uint32_t v = 0; v < ctx->V; v++) {
+        out->rays += s[4 * (size_t)v + 0];
+        out->probes_in += s[4 * (size_t)v + 1];
+        out->hits += s[4 * (size_t)v + 2];
+        out->steps += s[4 * (size_t)v + 3];
+    }
     return PRV_OK;
 }
 
@@ -1166,7 +1329,10 @@ int prv_get_timing(prv_ctx* ctx, prv_timing* out) {
         ms[s.cls] += t;
         cnt[s.cls] += s.launches;
     }
-    out->cast_ms = ms[K_CAST];       out->cast_launches = cnt[K_CAST];
+    out->cast_ms = ms[K_CAST] + ms[K_CULL] + ms[K_MARCH];
+    out->cast_launches = cnt[K_CAST] + cnt[K_CULL] + cnt[K_MARCH];
+    out->cull_ms = ms[K_CULL];       out->cull_launches = cnt[K_CULL];
+    out->march_ms = ms[K_MARCH];     out->march_launches = cnt[K_MARCH];
     out->project_ms = ms[K_PROJECT]; out->project_launches = cnt[K_PROJECT];
     out->count_ms = ms[K_COUNT];     out->count_launches = cnt[K_COUNT];
     out->greedy_ms = ms[K_GREEDY];   out->greedy_launches = cnt[K_GREEDY];
