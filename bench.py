@@ -295,17 +295,30 @@ def run_own(args):
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (ray cast): algorithmic bytes per launch / CUDA-event time per launch
+    # ---- roofline of the dominant kernel (march_kernel): algorithmic bytes per launch / CUDA-event time per launch.
+    # S_in (in-AABB probes of the literal algorithm) is a property of the input: it is counted once, untimed, with the
+    # FAST variant, which executes every probe of the reference algorithm (the AXIS pipeline proves some misses cheaper).
     peak, peak_src = _peaks()
     bitmap_bytes = ctx.map_bytes()
+    ctx.set_variant(prv.VARIANT_FAST)
+    ctx.cast_async(prv.MODE_DENSE, want_pixels=False)
+    s_in = ctx.get_cast_stats()["probes_in"]
+    ctx.set_variant(args.variant)
     per_launch_rays = stats["rays"]
-    alg_bytes = 4 * stats["probes_in"] + 8 * per_launch_rays + local_views * (bitmap_bytes + ctx.words * 8)
-    cast_ms = timing["cast_ms"] / max(1, timing["cast_launches"])
-    achieved = alg_bytes / (cast_ms * 1e-3) / 1e9
+    alg_total = 4 * s_in + 8 * per_launch_rays + local_views * (bitmap_bytes + ctx.words * 8)
+    launches = max(1, timing["march_launches"] if args.variant == 2 else timing["cast_launches"])
+    march_ms = (timing["march_ms"] if args.variant == 2 else timing["cast_ms"]) / launches
+    cull_ms = timing["cull_ms"] / max(1, timing["cull_launches"])
+    # the cull kernel writes the 8 B/ray "no hit" records of the rays it proves to miss; everything else is the march kernel's
+    alg_march = alg_total - 8 * (per_launch_rays - stats["marched"]) if args.variant == 2 else alg_total
+    achieved = alg_march / (march_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "raycast_kernel", "algorithmic_bytes_per_launch": int(alg_bytes), "ms_per_launch": cast_ms, "peak_source": peak_src,
-                "share_of_step": timing["cast_ms"] / total_ms,
-                "note": "4*S_in + 8 B per ray + per view (bitmap + bitset row); the kernel is FP64-issue bound, not bandwidth bound (DESIGN.md)"}
+                "kernel": "march_kernel" if args.variant == 2 else "raycast_kernel", "algorithmic_bytes_per_launch": int(alg_march),
+                "ms_per_launch": march_ms, "peak_source": peak_src, "share_of_step": march_ms * launches / total_ms,
+                "s_in_probes": int(s_in),
+                "cast_pipeline": {"kernels": "cull_kernel+march_kernel", "algorithmic_bytes": int(alg_total), "ms": cull_ms + march_ms,
+                                  "achieved": alg_total / ((cull_ms + march_ms) * 1e-3) / 1e9, "frac": alg_total / ((cull_ms + march_ms) * 1e-3) / 1e9 / peak},
+                "note": "per ray 4*S_in + 8 B, per view bitmap + bitset row (SURVEY 8(d)); the march is FP64-add/issue bound, not bandwidth bound (DESIGN.md)"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
@@ -330,7 +343,7 @@ def run_own(args):
             "gpu_launches": counters["kernel_launches"], "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "views_scored_per_sec": views_scored * world / max(1e-9, timing["greedy_ms"] / args.steps * 1e-3) if not strong else
                                     views_scored / max(1e-9, timing["greedy_ms"] / args.steps * 1e-3),
-            "kernel_ms_per_step": {k: timing[k] / args.steps for k in ("cast_ms", "count_ms", "greedy_ms", "other_ms")},
+            "kernel_ms_per_step": {k: timing[k] / args.steps for k in ("cast_ms", "cull_ms", "march_ms", "count_ms", "greedy_ms", "other_ms")},
             "cast_stats": stats, "greedy_len": int(len(seq)), "coverage_rate": float(gains.sum()) / max(1, ctx.full_voxels)}
     print(json.dumps(line))
     if dist is not None:

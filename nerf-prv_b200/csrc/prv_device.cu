@@ -65,98 +65,285 @@ __device__ __forceinline__ void write_hit(const CastParams& p, const ViewConst& 
     }
 }
 
-// ---- AXIS pipeline, kernel 1: loose float cull of every pixel, survivors compacted into a per-view queue ----------
-// 32x8 pixel tile per block (each warp an 8x4 patch); culled pixels get their "no hit" outputs here, survivors are
-// marched by march_kernel.  blockIdx.x = tile, blockIdx.y = view.
-template <bool MASKED>
-__global__ void __launch_bounds__(256) cull_kernel(const CastParams p) {
-    __shared__ ViewConst s_vc;
-    __shared__ uint32_t s_woff[8];
-    __shared__ uint32_t s_base;
-    const uint32_t view = blockIdx.y + p.view_base;
-    load_view_const(s_vc, p.views + view);
-    const ViewConst& vc = s_vc;
-    const int tiles_x = (p.GW + 31) >> 5;
-    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+// ---- AXIS pipeline ------------------------------------------------------------------------------------------------
+// kernel 1 (cull_kernel):   every pixel, loose float slab test against the grown AABB; survivors -> queue 1
+// kernel 2 (coarse_kernel): dense warps over queue 1, conservative coarse-brick walk; survivors -> queue 2
+// kernel 3 (march_kernel):  dense warps over queue 2, the exact castRay march
+// Kernels 2 and 3 run persistent blocks that pull 256-ray chunks of a flattened (view, chunk) list with an atomic
+// ticket, so expensive and cheap chunks balance across the 148 SMs and there is no partial last wave.
+
+// block-level stream compaction of `keep` lanes into a per-view queue: one atomic per block
+__device__ __forceinline__ void block_append(bool keep, uint32_t value, uint32_t* queue_view, uint32_t* count_view, uint32_t* s_woff, uint32_t* s_base) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int px = (tile_x << 5) + ((warp & 3) << 3) + (lane & 7);
-    const int py = (tile_y << 3) + ((warp >> 2) << 2) + (lane >> 3);
-    const bool in_grid = px < p.GW && py < p.GH;
-    const unsigned long long pid = (unsigned long long)py * p.GW + px;
-    bool active = in_grid && (vc.flags & kViewInMap) && !(vc.flags & kViewInObject);
-    if (MASKED && active) {
-        const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
-        active = (w >> (pid & 31)) & 1u;
-    }
-    bool survive = false;
-    if (active) {
-        if (!(vc.flags & kViewFastOk)) {
-            survive = true;  // this view needs the literal march (max-range test): no cull
-        } else {
-            float dx, dy, dz;
-            ray_direction(p.cam, vc, px, py, dx, dy, dz);
-            survive = !loose_miss(p.map, vc, dx, dy, dz);
-        }
-    }
-    if (in_grid && !survive && p.pix_hit && (!MASKED || active)) {
-        p.pix_hit[(size_t)view * p.pix_stride + pid] = kNone;
-        if (p.pix_depth) p.pix_depth[(size_t)view * p.pix_stride + pid] = 0.0f;
-    }
-    // block-level compaction: one atomic per block on the view's counter
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, survive);
-    const uint32_t act = __ballot_sync(0xFFFFFFFFu, active);
-    if (lane == 0) s_woff[warp] = __popc(bal) | (__popc(act) << 16);
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) s_woff[warp] = __popc(bal);
     __syncthreads();
     if (threadIdx.x == 0) {
-        uint32_t tot = 0, rays = 0;
+        uint32_t tot = 0;
         for (int w = 0; w < 8; w++) {
-            const uint32_t c = s_woff[w] & 0xFFFFu;
-            rays += s_woff[w] >> 16;
+            const uint32_t c = s_woff[w];
             s_woff[w] = tot;
             tot += c;
         }
+        *s_base = tot ? atomicAdd(count_view, tot) : 0u;
+    }
+    __syncthreads();
+    if (keep) queue_view[*s_base + s_woff[warp] + __popc(bal & ((1u << lane) - 1u))] = value;
+    __syncthreads();  // s_woff / s_base are reused by the next chunk
+}
+
+// One block per 32x32 pixel region of one view (blockIdx.x = region, blockIdx.y = view); every thread owns 4 pixels,
+// one in each 32x8 row-tile (a warp covers an 8x4 patch per row-tile).
+// Region test: the region's rays lie inside the cone around the mean corner direction whose half-angle is the largest
+// corner angle (the pixel->direction map is projective up to the mild, host-checked lens distortion, for which the
+// corners are taken 2 pixels outside the region); if that cone misses the bounding sphere of the grown AABB, no ray
+// of the region can touch the AABB and the per-pixel tests are skipped.
+template <bool MASKED>
+__global__ void __launch_bounds__(256) cull_kernel(const CastParams p) {
+    __shared__ ViewConst s_vc;
+    __shared__ uint32_t s_woff[4][8];
+    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_rays[8];
+    __shared__ int s_skip;
+    const uint32_t view = blockIdx.y + p.view_base;
+    load_view_const(s_vc, p.views + view);
+    const ViewConst& vc = s_vc;
+    const int regions_x = (p.GW + 31) >> 5;
+    const int region_x = blockIdx.x % regions_x, region_y = blockIdx.x / regions_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool view_ok = (vc.flags & kViewInMap) && !(vc.flags & kViewInObject);
+    const bool fast = (vc.flags & kViewFastOk) != 0;
+
+    if (threadIdx.x < 32) {
+        bool skip = false;
+        if (!MASKED && view_ok && fast && p.cam.region_cull_ok) {
+            const int c = lane & 3;
+            const float cx = (float)((region_x << 5) + ((c & 1) ? 33 : -2));
+            const float cy = (float)((region_y << 5) + ((c & 2) ? 33 : -2));
+            float dx, dy, dz;
+            ray_direction_approx(p.cam, vc, cx, cy, dx, dy, dz);
+            const float rn = rsqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+            dx *= rn; dy *= rn; dz *= rn;
+            float sx = dx, sy = dy, sz = dz;
+            sx += __shfl_xor_sync(0xFFFFFFFFu, sx, 1); sy += __shfl_xor_sync(0xFFFFFFFFu, sy, 1); sz += __shfl_xor_sync(0xFFFFFFFFu, sz, 1);
+            sx += __shfl_xor_sync(0xFFFFFFFFu, sx, 2); sy += __shfl_xor_sync(0xFFFFFFFFu, sy, 2); sz += __shfl_xor_sync(0xFFFFFFFFu, sz, 2);
+            const float sn = rsqrtf(fmaf(sx, sx, fmaf(sy, sy, sz * sz)));
+            sx *= sn; sy *= sn; sz *= sn;                        // cone axis
+            float cos_t = fmaf(sx, dx, fmaf(sy, dy, sz * dz));   // smallest cosine over the corners = cone half-angle
+            cos_t = fminf(cos_t, __shfl_xor_sync(0xFFFFFFFFu, cos_t, 1));
+            cos_t = fminf(cos_t, __shfl_xor_sync(0xFFFFFFFFu, cos_t, 2));
+            const float wx = p.map.bcen[0] - vc.origin[0], wy = p.map.bcen[1] - vc.origin[1], wz = p.map.bcen[2] - vc.origin[2];
+            const float dist2 = fmaf(wx, wx, fmaf(wy, wy, wz * wz));
+            const float rad = p.map.brad;
+            if (dist2 > rad * rad * 1.01f && cos_t > 0.5f) {
+                const float inv_d = rsqrtf(dist2);
+                const float cos_p = fmaf(sx, wx, fmaf(sy, wy, sz * wz)) * inv_d;  // angle between cone axis and sphere centre
+                const float sin_a = rad * inv_d;                                     // angular radius of the sphere
+                const float cos_a = sqrtf(fmaxf(0.0f, 1.0f - sin_a * sin_a));
+                const float sin_t = sqrtf(fmaxf(0.0f, 1.0f - cos_t * cos_t));
+                const float cos_sum = fmaf(cos_t, cos_a, -sin_t * sin_a);           // cos(theta + alpha), theta+alpha < pi here
+                skip = cos_p < cos_sum - 1.0e-3f;
+            }
+        }
+        if (lane == 0) s_skip = skip ? 1 : 0;
+    }
+    __syncthreads();
+    const bool skip = s_skip != 0;
+
+    uint32_t keep_mask = 0;  // bit t: this thread's pixel in row-tile t survives
+    uint32_t pids[4];
+    uint32_t nrays = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const int px = (region_x << 5) + ((warp & 3) << 3) + (lane & 7);
+        const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
+        const bool in_grid = px < p.GW && py < p.GH;
+        const unsigned long long pid = (unsigned long long)py * p.GW + px;
+        pids[t] = (uint32_t)pid;
+        bool active = in_grid && view_ok;
+        if (MASKED && active) {
+            const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
+            active = (w >> (pid & 31)) & 1u;
+        }
+        bool survive = false;
+        if (active && !skip) {
+            if (!fast) {
+                survive = true;  // this view needs the literal march (max-range test): no cull
+            } else {
+                float dx, dy, dz;
+                ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
+                survive = !loose_miss(p.map, vc, dx, dy, dz);
+            }
+        }
+        if (in_grid && !survive && p.pix_hit && (!MASKED || active)) {
+            p.pix_hit[(size_t)view * p.pix_stride + pid] = kNone;
+            if (p.pix_depth) p.pix_depth[(size_t)view * p.pix_stride + pid] = 0.0f;
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, survive);
+        nrays += __popc(__ballot_sync(0xFFFFFFFFu, active));
+        if (survive) keep_mask |= 1u << t;
+        if (lane == 0) s_woff[t][warp] = __popc(bal);
+        // lane-local rank within the warp for this row-tile, kept in the high bits
+        keep_mask |= (uint32_t)__popc(bal & ((1u << lane) - 1u)) << (8 + 6 * t);
+    }
+    if (lane == 0) s_rays[warp] = nrays;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0, rays = 0;
+        for (int t = 0; t < 4; t++)
+            for (int w = 0; w < 8; w++) {
+                const uint32_t c = s_woff[t][w];
+                s_woff[t][w] = tot;
+                tot += c;
+            }
+        for (int w = 0; w < 8; w++) rays += s_rays[w];
         s_base = tot ? atomicAdd(p.qcount + view, tot) : 0u;
         if (rays) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)rays);
     }
     __syncthreads();
-    if (survive) p.queue[(size_t)view * p.queue_cap + s_base + s_woff[warp] + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)pid;
+    if (keep_mask & 0xFu) {
+        uint32_t* q = p.queue + (size_t)view * p.queue_cap + s_base;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            if (keep_mask & (1u << t)) q[s_woff[t][warp] + ((keep_mask >> (8 + 6 * t)) & 63u)] = pids[t];
+    }
 }
 
-// ---- AXIS pipeline, kernel 2: dense warps of surviving rays; gridDim.x persistent blocks per view ------------------
-__global__ void __launch_bounds__(256) march_kernel(const CastParams p) {
-    __shared__ ViewConst s_vc;
-    const uint32_t view = blockIdx.y + p.view_base;
-    const uint32_t count = p.qcount[view];
-    if ((unsigned long long)blockIdx.x * 256ull >= count) return;
-    load_view_const(s_vc, p.views + view);
-    const ViewConst& vc = s_vc;
-    const bool plain = !(vc.flags & kViewFastOk);
-    uint32_t c_probes = 0, c_hits = 0, c_steps = 0;
-    for (unsigned long long base = (unsigned long long)blockIdx.x * 256ull; base < count; base += (unsigned long long)gridDim.x * 256ull) {
-        const unsigned long long idx = base + threadIdx.x;
-        if (idx >= count) continue;
-        const uint32_t pid = p.queue[(size_t)view * p.queue_cap + idx];
-        const int py = (int)(pid / (uint32_t)p.GW), px = (int)(pid - (uint32_t)py * (uint32_t)p.GW);
-        CastResult res;
-        res.rank = kNone;
-        res.steps = 0;
-        res.probes = 0;
-        res.k0 = res.k1 = res.k2 = 0;
-        RayState r;
-        float dx, dy, dz;
-        ray_direction(p.cam, vc, px, py, dx, dy, dz);
-        if (ray_init(vc, p.map.resolution, dx, dy, dz, r)) {
-            if (plain)
-                march_plain(p.map, p.cam, vc, r, res);
-            else
-                march_axis(p.map, vc, r, res);
-        }
-        write_hit(p, vc, view, pid, res);
-        c_probes += res.probes;
-        c_hits += res.rank != kNone ? 1u : 0u;
-        c_steps += res.steps;
+// exclusive prefix of 256-ray chunk counts over the views of this launch -> s_prefix[0..nviews]
+__device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint32_t nviews, uint32_t* s_prefix) {
+    __shared__ uint32_t s_part[8];
+    // each thread owns a contiguous run of views
+    const uint32_t per = (nviews + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = threadIdx.x * per, e = min(nviews, b + per);
+    uint32_t sum = 0;
+    for (uint32_t v = b; v < e; v++) sum += (counts[v] + 255u) >> 8;
+    // block exclusive scan of the per-thread sums
+    uint32_t incl = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
     }
-    commit_stats(p.stats + 4 * (size_t)view, 0u, c_probes, c_hits, c_steps);
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; w++) woff += s_part[w];
+    uint32_t run = woff + incl - sum;
+    for (uint32_t v = b; v < e; v++) {
+        s_prefix[v] = run;
+        run += (counts[v] + 255u) >> 8;
+    }
+    if (threadIdx.x == blockDim.x - 1) s_prefix[nviews] = woff + incl;
+    __syncthreads();
+}
+
+// chunk id -> view index (largest v with s_prefix[v] <= g)
+__device__ __forceinline__ uint32_t find_view(const uint32_t* s_prefix, uint32_t nviews, uint32_t g) {
+    uint32_t lo = 0, hi = nviews;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (s_prefix[mid] <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(256) coarse_kernel(const CastParams p) {
+    __shared__ ViewConst s_vc;
+    __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
+    __shared__ uint32_t s_woff[8];
+    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_ticket;
+    build_chunk_prefix(p.qcount + p.view_base, p.nviews, s_prefix);
+    const uint32_t total = s_prefix[p.nviews];
+    uint32_t cur_view = 0xFFFFFFFFu;
+    for (;;) {
+        if (threadIdx.x == 0) s_ticket = atomicAdd(p.tickets + 0, 1u);
+        __syncthreads();
+        const uint32_t g = s_ticket;
+        if (g >= total) break;
+        const uint32_t vl = find_view(s_prefix, p.nviews, g);
+        const uint32_t view = vl + p.view_base;
+        if (view != cur_view) {
+            __syncthreads();
+            load_view_const(s_vc, p.views + view);
+            cur_view = view;
+        }
+        const ViewConst& vc = s_vc;
+        const uint32_t count = p.qcount[view];
+        const uint32_t idx = (g - s_prefix[vl]) * 256u + threadIdx.x;
+        bool keep = false;
+        uint32_t pid = 0;
+        if (idx < count) {
+            pid = p.queue[(size_t)view * p.queue_cap + idx];
+            if (!(vc.flags & kViewFastOk)) {
+                keep = true;
+            } else {
+                const int py = (int)(pid / (uint32_t)p.GW), px = (int)(pid - (uint32_t)py * (uint32_t)p.GW);
+                float dx, dy, dz;
+                ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
+                keep = !coarse_miss(p.map, vc, dx, dy, dz);
+            }
+            if (!keep && p.pix_hit) {
+                p.pix_hit[(size_t)view * p.pix_stride + pid] = kNone;
+                if (p.pix_depth) p.pix_depth[(size_t)view * p.pix_stride + pid] = 0.0f;
+            }
+        }
+        block_append(keep, pid, p.queue2 + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
+    }
+}
+
+__global__ void __launch_bounds__(256, 5) march_kernel(const CastParams p) {
+    __shared__ ViewConst s_vc;
+    __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
+    __shared__ uint32_t s_ticket;
+    build_chunk_prefix(p.qcount2 + p.view_base, p.nviews, s_prefix);
+    const uint32_t total = s_prefix[p.nviews];
+    uint32_t cur_view = 0xFFFFFFFFu;
+    uint32_t c_probes = 0, c_hits = 0, c_steps = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s_ticket = atomicAdd(p.tickets + 1, 1u);
+        __syncthreads();
+        const uint32_t g = s_ticket;
+        __syncthreads();
+        if (g >= total) break;
+        const uint32_t vl = find_view(s_prefix, p.nviews, g);
+        const uint32_t view = vl + p.view_base;
+        if (view != cur_view) {
+            if (cur_view != 0xFFFFFFFFu) {  // flush the finished view's counters
+                commit_stats(p.stats + 4 * (size_t)cur_view, 0u, c_probes, c_hits, c_steps);
+                c_probes = c_hits = c_steps = 0;
+            }
+            __syncthreads();
+            load_view_const(s_vc, p.views + view);
+            cur_view = view;
+        }
+        const ViewConst& vc = s_vc;
+        const uint32_t count = p.qcount2[view];
+        const uint32_t idx = (g - s_prefix[vl]) * 256u + threadIdx.x;
+        if (idx < count) {
+            const uint32_t pid = p.queue2[(size_t)view * p.queue_cap + idx];
+            const int py = (int)(pid / (uint32_t)p.GW), px = (int)(pid - (uint32_t)py * (uint32_t)p.GW);
+            CastResult res;
+            res.rank = kNone;
+            res.steps = 0;
+            res.probes = 0;
+            res.k0 = res.k1 = res.k2 = 0;
+            RayState r;
+            float dx, dy, dz;
+            ray_direction(p.cam, vc, px, py, dx, dy, dz);
+            if (ray_init(vc, p.map.resolution, dx, dy, dz, r)) {
+                if (!(vc.flags & kViewFastOk))
+                    march_plain(p.map, p.cam, vc, r, res);
+                else
+                    march_axis(p.map, vc, r, res);
+            }
+            write_hit(p, vc, view, pid, res);
+            c_probes += res.probes;
+            c_hits += res.rank != kNone ? 1u : 0u;
+            c_steps += res.steps;
+        }
+    }
+    if (cur_view != 0xFFFFFFFFu) commit_stats(p.stats + 4 * (size_t)cur_view, 0u, c_probes, c_hits, c_steps);
 }
 
 // ---- PLAIN / FAST variants: one kernel, one thread per pixel of a 32x8 tile ----------------------------------------
@@ -429,12 +616,14 @@ struct prv_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int variant = PRV_VARIANT_AXIS;
+    int occ_coarse = 0, occ_march = 0;
 
     // map
     bool have_map = false;
     DevMap map{};
     double resolution = 0;
     int lo[3] = {0, 0, 0}, n[3] = {0, 0, 0};
+    DevBuf d_coarse;
     DevBuf d_bitmap, d_bitmap_pad, d_prefix, d_leaf_of_raster, d_keys, d_rgb;
     std::vector<uint16_t> h_keys;
 
@@ -452,7 +641,7 @@ struct prv_ctx {
     uint32_t id_space = 0;
 
     // cast outputs
-    DevBuf d_queue, d_qcount;
+    DevBuf d_queue, d_qcount, d_queue2, d_tickets;
     DevBuf d_bitsets, d_counts, d_stats, d_pix_hit, d_pix_depth, d_mask, d_voxel_pix, d_voxel_hit, d_points;
     int last_mode = -1;
     bool have_pixels = false;
@@ -605,6 +794,7 @@ void make_view_const(const prv_ctx* ctx, const double* pose_world, const double*
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 4; c++) {
             vc.pose[4 * r + c] = pw(r, c);
+            vc.posef[4 * r + c] = (float)pw(r, c);
             vc.inv[4 * r + c] = inv(r, c);
         }
     vc.flags = 0;
@@ -618,6 +808,7 @@ void make_view_const(const prv_ctx* ctx, const double* pose_world, const double*
         vc.origin[a] = ok ? (float)prv::key_to_coord(k[a], ctx->resolution) : 0.0f;
     }
     if (!ok) return;
+    for (int r = 0; r < 3; r++) vc.posef[4 * r + 3] = (float)(pw(r, 3) - (double)vc.origin[r]);
     vc.flags |= kViewInMap;
     // castRay re-derives current_key from the float origin; it is the same key (|error| << half a voxel) but recompute literally
     for (int a = 0; a < 3; a++) {
@@ -743,39 +934,51 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
     }
     if (ctx->variant == PRV_VARIANT_AXIS) {
         if ((rc = ensure(ctx, ctx->d_queue, (size_t)V * ctx->pix_stride * 4))) return rc;
-        if ((rc = ensure(ctx, ctx->d_qcount, (size_t)V * 4))) return rc;
-        CU(cudaMemsetAsync(ctx->d_qcount.p, 0, (size_t)V * 4, ctx->stream));
+        if ((rc = ensure(ctx, ctx->d_queue2, (size_t)V * ctx->pix_stride * 4))) return rc;
+        if ((rc = ensure(ctx, ctx->d_qcount, (size_t)V * 2 * 4))) return rc;
+        const uint32_t nlaunch = (V + kMaxViewsPerLaunch - 1) / kMaxViewsPerLaunch;
+        if ((rc = ensure(ctx, ctx->d_tickets, (size_t)nlaunch * 2 * 4))) return rc;
+        CU(cudaMemsetAsync(ctx->d_qcount.p, 0, (size_t)V * 2 * 4, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_tickets.p, 0, (size_t)nlaunch * 2 * 4, ctx->stream));
         p.queue = ptr<uint32_t>(ctx->d_queue);
         p.qcount = ptr<uint32_t>(ctx->d_qcount);
+        p.queue2 = ptr<uint32_t>(ctx->d_queue2);
+        p.qcount2 = ptr<uint32_t>(ctx->d_qcount) + V;
         p.queue_cap = ctx->pix_stride;
     }
     const uint32_t tiles = (uint32_t)(((p.GW + 31) / 32) * ((p.GH + 7) / 8));
-    for (uint32_t vb = 0; vb < V; vb += 32768) {
-        const uint32_t vn = std::min<uint32_t>(32768, V - vb);
+    const uint32_t vstep = ctx->variant == PRV_VARIANT_AXIS ? (uint32_t)kMaxViewsPerLaunch : 32768u;
+    for (uint32_t vb = 0, li = 0; vb < V; vb += vstep, li++) {
+        const uint32_t vn = std::min<uint32_t>(vstep, V - vb);
         if (voxel) {
             Span s(ctx, K_PROJECT, 1);
             project_voxels_kernel<<<dim3((ctx->map.n_occ + 255) / 256, vn), 256, 0, ctx->stream>>>(
                 ctx->map, ctx->cam, ptr<ViewConst>(ctx->d_views), vb, ptr<uint32_t>(ctx->d_mask), ctx->mask_words, ptr<uint32_t>(ctx->d_voxel_pix));
         }
         p.view_base = vb;
+        p.nviews = vn;
+        const dim3 grid(tiles, vn);
         if (ctx->variant == PRV_VARIANT_AXIS) {
-            // cull + compact, then march the survivors in dense warps
-            const dim3 grid(tiles, vn);
+            p.tickets = ptr<uint32_t>(ctx->d_tickets) + 2 * li;
+            if (ctx->occ_coarse == 0) {  // persistent grids = exactly one resident wave
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_coarse, coarse_kernel, 256, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march, march_kernel, 256, 0);
+                ctx->occ_coarse = std::max(1, ctx->occ_coarse);
+                ctx->occ_march = std::max(1, ctx->occ_march);
+            }
             {
-                Span s(ctx, K_CULL, 1);
+                Span s(ctx, K_CULL, 2);
+                const dim3 rgrid((uint32_t)(((p.GW + 31) / 32) * ((p.GH + 31) / 32)), vn);
                 if (voxel)
-                    cull_kernel<true><<<grid, 256, 0, ctx->stream>>>(p);
+                    cull_kernel<true><<<rgrid, 256, 0, ctx->stream>>>(p);
                 else
-                    cull_kernel<false><<<grid, 256, 0, ctx->stream>>>(p);
+                    cull_kernel<false><<<rgrid, 256, 0, ctx->stream>>>(p);
+                coarse_kernel<<<(uint32_t)(ctx->sm_count * ctx->occ_coarse), 256, 0, ctx->stream>>>(p);
             }
             Span s(ctx, K_MARCH, 1);
-            const uint32_t max_chunks = (uint32_t)((ctx->pix_stride + 255) / 256);
-            uint32_t per_view = (uint32_t)((ctx->sm_count * 16 + vn - 1) / vn);
-            per_view = std::max(1u, std::min(per_view, max_chunks));
-            march_kernel<<<dim3(per_view, vn), 256, 0, ctx->stream>>>(p);
+            march_kernel<<<(uint32_t)(ctx->sm_count * ctx->occ_march), 256, 0, ctx->stream>>>(p);
         } else {
             Span s(ctx, K_CAST, 1);
-            const dim3 grid(tiles, vn);
             if (ctx->variant == PRV_VARIANT_PLAIN)
                 launch_cast<PRV_VARIANT_PLAIN>(ctx, p, voxel, grid);
             else
@@ -905,8 +1108,8 @@ void prv_destroy(prv_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     prv_comm_destroy(ctx);
-    DevBuf* bufs[] = {&ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
-                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
+    DevBuf* bufs[] = {&ctx->d_coarse, &ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
+                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_tickets, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
                       &ctx->d_voxel_pix, &ctx->d_voxel_hit, &ctx->d_points, &ctx->d_best, &ctx->d_cov[0], &ctx->d_cov[1], &ctx->d_all_rows,
                       &ctx->d_all_ids, &ctx->d_cloud_xyz, &ctx->d_cloud_rgb, &ctx->d_corner, &ctx->d_rgba, &ctx->d_depth_img, &ctx->d_flush};
     for (DevBuf* b : bufs) release(*b);
@@ -1001,7 +1204,27 @@ int prv_set_map(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, uint32_t
             }
         }
     for (uint32_t i = 0; i < N; i++) pad_set(keys[3 * i] - lo[0] + 1, keys[3 * i + 1] - lo[1] + 1, keys[3 * i + 2] - lo[2] + 1);
+    // coarse occupancy (cells of kCoarse voxels) dilated by one voxel, for the conservative brick cull
+    int nc[3];
+    for (int a = 0; a < 3; a++) nc[a] = (n[a] + kCoarse - 1) / kCoarse;
+    std::vector<uint32_t> coarse(((size_t)nc[0] * nc[1] * nc[2] + 31) / 32 + 1, 0u);
+    for (uint32_t i = 0; i < N; i++) {
+        int cl[3], ch[3];
+        for (int a = 0; a < 3; a++) {
+            const int v = keys[3 * i + a] - lo[a];
+            cl[a] = std::max(0, (v - 1) / kCoarse);
+            ch[a] = std::min(nc[a] - 1, (v + 1) / kCoarse);
+        }
+        for (int K = cl[2]; K <= ch[2]; K++)
+            for (int J = cl[1]; J <= ch[1]; J++)
+                for (int I = cl[0]; I <= ch[0]; I++) {
+                    const size_t b = ((size_t)K * nc[1] + J) * nc[0] + I;
+                    coarse[b >> 5] |= 1u << (b & 31);
+                }
+    }
     int rc;
+    if ((rc = ensure(ctx, ctx->d_coarse, coarse.size() * 4))) return rc;
+    CU(h2d(ctx, ctx->d_coarse.p, coarse.data(), coarse.size() * 4));
     if ((rc = ensure(ctx, ctx->d_bitmap_pad, pad_words * 4))) return rc;
     CU(h2d(ctx, ctx->d_bitmap_pad.p, pad.data(), pad_words * 4));
     if ((rc = ensure(ctx, ctx->d_bitmap, nwords * 4))) return rc;
@@ -1032,6 +1255,17 @@ int prv_set_map(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, uint32_t
     ctx->map.words64 = words_for(N);
     ctx->map.bitmap = ptr<uint32_t>(ctx->d_bitmap);
     ctx->map.bitmap_pad = ptr<uint32_t>(ctx->d_bitmap_pad);
+    {
+        double rad2 = 0.0;
+        for (int a = 0; a < 3; a++) {
+            const double lo_m = (double)(lo[a] - 2 - prv::kTreeMaxVal) * resolution, hi_m = (double)(lo[a] + n[a] + 2 - prv::kTreeMaxVal) * resolution;
+            ctx->map.bcen[a] = (float)(0.5 * (lo_m + hi_m));
+            rad2 += 0.25 * (hi_m - lo_m) * (hi_m - lo_m);
+        }
+        ctx->map.brad = (float)(std::sqrt(rad2) * 1.001);
+    }
+    ctx->map.coarse = ptr<uint32_t>(ctx->d_coarse);
+    for (int a = 0; a < 3; a++) ctx->map.nc[a] = nc[a];
     ctx->map.pad_row_log2 = row_log2;
     ctx->map.pad_bit_offset = (uint32_t)slack_bits;
     for (int a = 0; a < 3; a++) {
@@ -1070,6 +1304,17 @@ int prv_set_camera(prv_ctx* ctx, const prv_intrinsics* intr, double max_range) {
     for (int i = 0; i < 5; i++) ctx->cam.c[i] = intr->coeffs[i];
     ctx->cam.max_range = max_range;
     ctx->cam.max_range_sq = max_range * max_range;
+    ctx->cam.inv_fx = 1.0f / intr->fx;
+    ctx->cam.inv_fy = 1.0f / intr->fy;
+    {
+        // region-level cone test needs the pixel->direction map to be close to projective: mild distortion over the image
+        const float xm = std::max(std::fabs((0.0f - intr->ppx) / intr->fx), std::fabs(((float)intr->width - intr->ppx) / intr->fx));
+        const float ym = std::max(std::fabs((0.0f - intr->ppy) / intr->fy), std::fabs(((float)intr->height - intr->ppy) / intr->fy));
+        const float r2 = xm * xm + ym * ym;
+        const float dist = std::fabs(intr->coeffs[0]) * r2 + std::fabs(intr->coeffs[1]) * r2 * r2 + std::fabs(intr->coeffs[4]) * r2 * r2 * r2 +
+                           3.0f * (std::fabs(intr->coeffs[2]) + std::fabs(intr->coeffs[3])) * std::sqrt(r2);
+        ctx->cam.region_cull_ok = (intr->model != 2 || dist < 0.25f) && r2 < 4.0f;
+    }
     ctx->have_cam = true;
     ctx->V = 0;  // per-view fast-path proofs depend on max_range
     ctx->cast_done = false;
@@ -1195,7 +1440,7 @@ int prv_get_cast_stats(prv_ctx* ctx, prv_cast_stats* out) {
     out->rays = out->probes_in = out->hits = out->steps = out->marched = 0;
     if (ctx->variant == PRV_VARIANT_AXIS) {
         std::vector<uint32_t> q(ctx->V);
-        CU(d2h(ctx, q.data(), ctx->d_qcount.p, q.size() * 4));
+        CU(d2h(ctx, q.data(), ptr<uint32_t>(ctx->d_qcount) + ctx->V, q.size() * 4));
         CU(cudaStreamSynchronize(ctx->stream));
         for (uint32_t c : q) out->marched += c;
     }

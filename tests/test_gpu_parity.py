@@ -48,7 +48,10 @@ def test_dense_matches_oracle(prv, orc, synth, ctx, name, n_views, size, variant
     assert np.array_equal(depth, o_depth)  # in fact identical
     st = ctx.get_cast_stats()
     assert st["hits"] == o_st["hits"] and st["rays"] == o_st["rays"]
-    assert st["probes_in"] == o_st["probes_in"], "S_in (in-AABB probes) must equal the oracle's count"
+    if variant == 2:  # AXIS proves some through-AABB misses without marching them (conservative brick cull)
+        assert st["probes_in"] <= o_st["probes_in"] and st["marched"] >= st["hits"]
+    else:
+        assert st["probes_in"] == o_st["probes_in"], "S_in (in-AABB probes) must equal the oracle's count"
     assert (hit != prv.NONE).sum() > 100  # the scene is actually visible
 
 
@@ -210,7 +213,11 @@ def test_full_size_properties_C1(prv, synth, ctx):
             ref = (bits, hit, depth, st)
         else:
             assert np.array_equal(bits, ref[0]) and np.array_equal(hit, ref[1]) and np.array_equal(depth, ref[2])
-            assert st["probes_in"] == ref[3]["probes_in"] and st["hits"] == ref[3]["hits"]
+            assert st["hits"] == ref[3]["hits"]
+            if variant == 1:
+                assert st["probes_in"] == ref[3]["probes_in"]
+            else:
+                assert st["probes_in"] <= ref[3]["probes_in"]
     assert st["rays"] == 32 * 640 * 480
     seq, gain = ctx.greedy(0, 64)
     assert len(set(seq.tolist())) == len(seq) and gain[1:].tolist() == sorted(gain[1:].tolist(), reverse=True)
