@@ -25,6 +25,15 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "rays_per_sec"
 UNIT = "rays/s"
 GREEDY_MAX_ITER = 64  # DefaultConfiguration.yaml:26 num_of_max_iteration
@@ -149,7 +158,7 @@ def run_reference(args):
             "data": "synthetic", "config": _config(w, args, world),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -173,6 +182,7 @@ def run_own(args):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     strong = args.workload == "C3" and world > 1
+    from nerf_prv_b200 import sharding
     # every rank its own object (weak scaling) except in the C3 strong-scaling mode
     obj_index = rank if args.workload == "C4" else 0
     w = synth.build_workload(prv, args.workload, obj_index=obj_index)
@@ -182,9 +192,11 @@ def run_own(args):
     ctx.set_camera(w["intr"], 1.0)
     V = w["n_views"]
     if strong:
-        ids = np.arange(rank, V, world, dtype=np.uint32)  # interleaved view sharding
-        if len(ids) * world != V:
-            raise SystemExit("C3 strong scaling needs views divisible by world size")
+        ids = sharding.pad_view_ids(sharding.shard_view_ids(V, rank, world), V, rank, world)  # interleaved view sharding
+        real = ids < V
+        shard_pose = np.where(real[:, None, None], w["pose_world"][np.minimum(ids, V - 1)], np.eye(4)[None])
+        # padded slots: a position outside the key range -> "View out of map" -> empty coverage row
+        shard_init = np.where(real[:, None], w["init_pos"][np.minimum(ids, V - 1)], 1.0e6)
         if rank == 0:
             uid = prv.comm_unique_id()
         else:
@@ -193,8 +205,8 @@ def run_own(args):
         t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
         dist.broadcast(t, 0)
         ctx.comm_init(bytes(t.cpu().tolist()), rank, world)
-        ctx.set_views(w["pose_world"][ids], w["init_pos"][ids], view_ids=ids)
-        local_views = len(ids)
+        ctx.set_views(shard_pose, shard_init, view_ids=ids)
+        local_views = int(real.sum())
     else:
         ctx.set_views(w["pose_world"], w["init_pos"])
         local_views = V
@@ -239,15 +251,15 @@ def run_own(args):
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    rays_total = rays_per_step_local * world * args.steps
+    rays_total = (rays_per_step_local * world if not strong else V * w["W"] * w["H"]) * args.steps
     value = rays_total / (total_ms * 1e-3)
     seq, gains, _ = ctx.get_greedy(GREEDY_MAX_ITER)
     views_scored = sum(max(V - 1 - k, 0) for k in range(min(len(seq), GREEDY_MAX_ITER)))
 
     # ---- end-to-end through the host-buffer C ABI: H2D of the map + poses, D2H of bitsets, counts, greedy sequence
     e2e_steps = max(1, min(args.steps, 5))
-    pw = np.ascontiguousarray(w["pose_world"] if not strong else w["pose_world"][ids])
-    ip = np.ascontiguousarray(w["init_pos"] if not strong else w["init_pos"][ids])
+    pw = np.ascontiguousarray(w["pose_world"] if not strong else shard_pose)
+    ip = np.ascontiguousarray(w["init_pos"] if not strong else shard_init)
     try:
         import torch
         def pinned(a):
@@ -287,7 +299,7 @@ def run_own(args):
         t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
-    e2e_value = rays_per_step_local * world * e2e_steps / e2e_dt
+    e2e_value = (rays_per_step_local * world if not strong else V * w["W"] * w["H"]) * e2e_steps / e2e_dt
     assert e_seq.tolist() == seq.tolist(), "e2e and resident paths disagree"
 
     if rank != 0:
@@ -344,14 +356,21 @@ def run_own(args):
             "views_scored_per_sec": views_scored * world / max(1e-9, timing["greedy_ms"] / args.steps * 1e-3) if not strong else
                                     views_scored / max(1e-9, timing["greedy_ms"] / args.steps * 1e-3),
             "kernel_ms_per_step": {k: timing[k] / args.steps for k in ("cast_ms", "cull_ms", "march_ms", "count_ms", "greedy_ms", "other_ms")},
-            "cast_stats": stats, "greedy_len": int(len(seq)), "coverage_rate": float(gains.sum()) / max(1, ctx.full_voxels)}
-    print(json.dumps(line))
+            "cast_stats": stats, "greedy_len": int(len(seq)), "greedy_seq": [int(x) for x in seq], "coverage_rate": float(gains.sum()) / max(1, ctx.full_voxels)}
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything libraries print there (e.g. "NCCL version ...") goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

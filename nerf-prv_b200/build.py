@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libprv_b200.so")
 SOURCES = ["prv_device.cu", "prv_host.cpp"]
 DEPS = ["prv_kernels.cuh", "prv_keys.hpp", "../host/prv_linalg.hpp", "../host/View_Space.hpp", "../host/Share_Data.hpp",
-        "../../include/prv.h"]
+        "../host/Perception_3D.hpp", "../host/NBV_Net_Labeler.hpp", "../host/prv_io.hpp", "../host/prv_simulation.cpp", "../../include/prv.h"]
 
 
 def needs_build():
@@ -41,7 +41,24 @@ def build(force=False, verbose=False):
         sys.stderr.write(r.stdout)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building libprv_b200.so")
+    build_driver(verbose)
     return LIB
+
+
+DRIVER = os.path.join(HERE, "prv_simulation")
+
+
+def build_driver(verbose=False):
+    """The C++ host driver (reference stdin protocol, mode 3) on top of the C ABI."""
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    cmd = [gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-Wall", "-o", DRIVER, os.path.join(HERE, "host", "prv_simulation.cpp"),
+           "-L" + HERE, "-lprv_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0 or verbose:
+        sys.stderr.write(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed building prv_simulation")
+    return DRIVER
 
 
 if __name__ == "__main__":
