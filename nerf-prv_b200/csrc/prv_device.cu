@@ -92,6 +92,25 @@ __device__ __forceinline__ void block_append(bool keep, uint32_t value, uint32_t
     __syncthreads();  // s_woff / s_base are reused by the next chunk
 }
 
+__device__ __forceinline__ void block_append2(bool keep, uint2 value, uint2* queue_view, uint32_t* count_view, uint32_t* s_woff, uint32_t* s_base) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) s_woff[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 8; w++) {
+            const uint32_t c = s_woff[w];
+            s_woff[w] = tot;
+            tot += c;
+        }
+        *s_base = tot ? atomicAdd(count_view, tot) : 0u;
+    }
+    __syncthreads();
+    if (keep) queue_view[*s_base + s_woff[warp] + __popc(bal & ((1u << lane) - 1u))] = value;
+    __syncthreads();
+}
+
 // One block per 32x32 pixel region of one view (blockIdx.x = region, blockIdx.y = view); every thread owns 4 pixels,
 // one in each 32x8 row-tile (a warp covers an 8x4 patch per row-tile).
 // Region test: the region's rays lie inside the cone around the mean corner direction whose half-angle is the largest
@@ -513,6 +532,79 @@ __global__ void __launch_bounds__(256) greedy_iter_kernel(const uint64_t* rows, 
     if (threadIdx.x == 0) atomicMax(best + k, ((unsigned long long)t << 32) | (unsigned long long)(0xFFFFFFFFu - view_ids[blockIdx.x]));
 }
 
+// Whole greedy loop in ONE persistent kernel (cooperative launch: every block is resident).  Each block keeps the
+// covered mask in shared memory and scores its rows (row r -> block r mod gridDim) against it; the per-iteration argmax
+// is one 64-bit atomicMax per block followed by a grid barrier (monotonic arrival counter in global memory); every block
+// then ORs the winner's row into its own copy of the mask.  Same selection rule and results as greedy_iter_kernel.
+__global__ void __launch_bounds__(256) greedy_persistent_kernel(const uint64_t* __restrict__ rows, uint32_t words64, uint32_t nrows,
+                                                                const uint32_t* __restrict__ view_ids, const uint32_t* __restrict__ row_of_id,
+                                                                uint32_t first_row, uint32_t first_id, uint32_t max_iter, unsigned long long* best,
+                                                                uint64_t* cov_out, unsigned int* arrive) {
+    extern __shared__ uint64_t s_cov[];
+    __shared__ uint32_t s_red[8];
+    __shared__ unsigned long long s_best;
+    const uint32_t half = words64 / 2;
+    ulonglong2* cov2 = reinterpret_cast<ulonglong2*>(s_cov);
+    {
+        const ulonglong2* r0 = reinterpret_cast<const ulonglong2*>(rows + (size_t)first_row * words64);
+        uint32_t c = 0;
+        for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) {
+            const ulonglong2 v = r0[w];
+            cov2[w] = v;
+            c += __popcll(v.x) + __popcll(v.y);
+        }
+        const uint32_t t = block_reduce_sum(c, s_red);
+        if (blockIdx.x == 0 && threadIdx.x == 0) best[0] = ((unsigned long long)t << 32) | (unsigned long long)(0xFFFFFFFFu - first_id);
+        __syncthreads();
+    }
+    for (uint32_t k = 1; k <= max_iter; k++) {
+        unsigned long long local = 0ull;
+        for (uint32_t r = blockIdx.x; r < nrows; r += gridDim.x) {
+            const ulonglong2* rv = reinterpret_cast<const ulonglong2*>(rows + (size_t)r * words64);
+            uint32_t c = 0;
+            for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) {
+                const ulonglong2 v = rv[w];
+                const ulonglong2 cv = cov2[w];
+                c += __popcll(v.x & ~cv.x) + __popcll(v.y & ~cv.y);
+            }
+            const uint32_t t = block_reduce_sum(c, s_red);
+            if (threadIdx.x == 0) {
+                const unsigned long long packed = ((unsigned long long)t << 32) | (unsigned long long)(0xFFFFFFFFu - view_ids[r]);
+                local = packed > local ? packed : local;
+            }
+            __syncthreads();  // s_red reuse
+        }
+        // argmax across blocks + grid barrier
+        if (threadIdx.x == 0) {
+            atomicMax(best + k, local);
+            __threadfence();
+            atomicAdd(arrive, 1u);
+            const unsigned int target = k * gridDim.x;
+            while (*reinterpret_cast<volatile unsigned int*>(arrive) < target) {
+            }
+            __threadfence();
+            s_best = *reinterpret_cast<volatile unsigned long long*>(best + k);
+        }
+        __syncthreads();
+        const unsigned long long b = s_best;
+        if ((b >> 32) == 0ull) break;  // nothing left to gain: selection is over
+        const uint32_t rb = row_of_id[0xFFFFFFFFu - (uint32_t)(b & 0xFFFFFFFFull)];
+        const ulonglong2* rw = reinterpret_cast<const ulonglong2*>(rows + (size_t)rb * words64);
+        for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) {
+            const ulonglong2 v = rw[w];
+            ulonglong2 cv = cov2[w];
+            cv.x |= v.x;
+            cv.y |= v.y;
+            cov2[w] = cv;
+        }
+        __syncthreads();
+    }
+    if (blockIdx.x == 0) {
+        __syncthreads();
+        for (uint32_t w = threadIdx.x; w < words64; w += blockDim.x) cov_out[w] = s_cov[w];
+    }
+}
+
 // splat z-buffer -------------------------------------------------------------------------------------
 // Stage 1: one 64-bit atomicMin per point on the CORNER cell of its footprint; stage 2 takes the min over the
 // point_size x point_size corner cells that cover a pixel.  min is associative, so this equals point_size^2 atomics
@@ -616,7 +708,11 @@ struct prv_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int variant = PRV_VARIANT_AXIS;
-    int occ_coarse = 0, occ_march = 0;
+    int occ_coarse = 0, occ_march = 0, occ_greedy = 0;
+    uint32_t occ_greedy_words = 0;
+    bool greedy_persistent = false;
+    int greedy_blocks_per_sm = 2;
+    DevBuf d_arrive;
 
     // map
     bool have_map = false;
@@ -1016,13 +1112,40 @@ int greedy_impl(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter) {
     // row index of first_view in the active table
     const uint32_t first_row = ctx->h_row_of_id[first_view];
     if (first_row == kNone) return fail(ctx, PRV_ERR_INVALID, "prv_greedy: first_view %u is not a resident view id", first_view);
-    Span s(ctx, K_GREEDY, max_iter + 2);
-    greedy_init_kernel<<<1, 256, 0, ctx->stream>>>(ctx->g_rows, words, first_row, first_view, ptr<unsigned long long>(ctx->d_best));
-    for (uint32_t k = 1; k <= max_iter + 1; k++) {
-        const int cover_only = k == max_iter + 1;
-        greedy_iter_kernel<<<cover_only ? 1 : ctx->g_nrows, 256, 0, ctx->stream>>>(
-            ctx->g_rows, words, ids, row_of_id, k, ptr<unsigned long long>(ctx->d_best), ptr<uint64_t>(ctx->d_cov[(k - 1) & 1]),
-            ptr<uint64_t>(ctx->d_cov[k & 1]), cover_only);
+    const size_t cov_bytes = (size_t)words * 8;
+    if (cov_bytes <= 160 * 1024) {
+        // one persistent cooperative kernel
+        if (ctx->occ_greedy_words != words) {
+            CU(cudaFuncSetAttribute(greedy_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_bytes));
+            int occ = 0;
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, greedy_persistent_kernel, 256, cov_bytes));
+            ctx->occ_greedy = std::max(1, occ);
+            ctx->occ_greedy_words = words;
+        }
+        if ((rc = ensure(ctx, ctx->d_arrive, 4))) return rc;
+        CU(cudaMemsetAsync(ctx->d_arrive.p, 0, 4, ctx->stream));
+        uint32_t grid = std::min<uint32_t>(ctx->g_nrows, (uint32_t)(ctx->sm_count * std::min(ctx->occ_greedy, ctx->greedy_blocks_per_sm)));
+        grid = std::max(1u, grid);
+        const uint64_t* rows_p = ctx->g_rows;
+        uint32_t words_a = words, nrows_a = ctx->g_nrows, first_row_a = first_row, first_id_a = first_view, max_iter_a = max_iter;
+        unsigned long long* best_p = ptr<unsigned long long>(ctx->d_best);
+        uint64_t* cov_p = ptr<uint64_t>(ctx->d_cov[0]);
+        unsigned int* arrive_p = ptr<unsigned int>(ctx->d_arrive);
+        void* args[] = {(void*)&rows_p, (void*)&words_a, (void*)&nrows_a, (void*)&ids, (void*)&row_of_id, (void*)&first_row_a, (void*)&first_id_a,
+                        (void*)&max_iter_a, (void*)&best_p, (void*)&cov_p, (void*)&arrive_p};
+        Span s(ctx, K_GREEDY, 1);
+        CU(cudaLaunchCooperativeKernel((const void*)greedy_persistent_kernel, dim3(grid), dim3(256), args, cov_bytes, ctx->stream));
+        ctx->greedy_persistent = true;
+    } else {
+        Span s(ctx, K_GREEDY, max_iter + 2);
+        greedy_init_kernel<<<1, 256, 0, ctx->stream>>>(ctx->g_rows, words, first_row, first_view, ptr<unsigned long long>(ctx->d_best));
+        for (uint32_t k = 1; k <= max_iter + 1; k++) {
+            const int cover_only = k == max_iter + 1;
+            greedy_iter_kernel<<<cover_only ? 1 : ctx->g_nrows, 256, 0, ctx->stream>>>(
+                ctx->g_rows, words, ids, row_of_id, k, ptr<unsigned long long>(ctx->d_best), ptr<uint64_t>(ctx->d_cov[(k - 1) & 1]),
+                ptr<uint64_t>(ctx->d_cov[k & 1]), cover_only);
+        }
+        ctx->greedy_persistent = false;
     }
     CU(cudaGetLastError());
     ctx->greedy_max_iter = max_iter;
@@ -1109,7 +1232,7 @@ void prv_destroy(prv_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     prv_comm_destroy(ctx);
     DevBuf* bufs[] = {&ctx->d_coarse, &ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
-                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_tickets, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
+                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_tickets, &ctx->d_arrive, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
                       &ctx->d_voxel_pix, &ctx->d_voxel_hit, &ctx->d_points, &ctx->d_best, &ctx->d_cov[0], &ctx->d_cov[1], &ctx->d_all_rows,
                       &ctx->d_all_ids, &ctx->d_cloud_xyz, &ctx->d_cloud_rgb, &ctx->d_corner, &ctx->d_rgba, &ctx->d_depth_img, &ctx->d_flush};
     for (DevBuf* b : bufs) release(*b);
@@ -1424,7 +1547,7 @@ int prv_get_greedy(prv_ctx* ctx, uint32_t* seq, uint32_t* gains, uint32_t* n_out
     }
     *n_out = n;
     if (covered_out) {
-        CU(d2h(ctx, covered_out, ctx->d_cov[n & 1].p, 8 * (size_t)ctx->map.words64));
+        CU(d2h(ctx, covered_out, ctx->d_cov[ctx->greedy_persistent ? 0 : (n & 1)].p, 8 * (size_t)ctx->map.words64));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return PRV_OK;
