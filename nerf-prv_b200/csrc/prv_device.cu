@@ -167,7 +167,27 @@ __global__ void __launch_bounds__(256) cull_kernel(const CastParams p) {
         if (lane == 0) s_skip = skip ? 1 : 0;
     }
     __syncthreads();
-    const bool skip = s_skip != 0;
+    if (s_skip != 0) {
+        // the whole region provably misses: record "no hit" for its pixels and leave (no compaction protocol)
+        if (p.pix_hit) {
+            const int px = (region_x << 5) + ((warp & 3) << 3) + (lane & 7);
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
+                if (px < p.GW && py < p.GH) {
+                    const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
+                    p.pix_hit[o] = kNone;
+                    if (p.pix_depth) p.pix_depth[o] = 0.0f;
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+            const int w = min(32, p.GW - (region_x << 5)), h = min(32, p.GH - (region_y << 5));
+            atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)(w * h));
+        }
+        return;
+    }
+    const bool skip = false;
 
     uint32_t keep_mask = 0;  // bit t: this thread's pixel in row-tile t survives
     uint32_t pids[4];
@@ -473,6 +493,101 @@ __device__ __forceinline__ uint32_t block_reduce_sum(uint32_t v, uint32_t* s_red
         for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xFFFFFFFFu, t, o);
     }
     return t;  // valid in thread 0
+}
+
+// ground-truth map build on the GPU (replaces the CPU octree insertion as far as the cast needs it) ------------------
+struct MapBuild {
+    int lo[3], n[3], wx, row_log2, nc[3];
+    uint32_t n_occ;
+    unsigned long long slack_bits, nwords;
+    uint32_t* bitmap;
+    uint32_t* pad;
+    uint32_t* coarse;
+    uint32_t* prefix;
+    uint32_t* leaf_of_raster;
+    const uint16_t* keys;
+};
+
+// per occupied voxel: occupancy bit, padded-bitmap bit, and the (<= 8) coarse cells within one voxel of it
+__global__ void __launch_bounds__(256) map_scatter_kernel(MapBuild b) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n_occ) return;
+    const int q0 = b.keys[3 * i] - b.lo[0], q1 = b.keys[3 * i + 1] - b.lo[1], q2 = b.keys[3 * i + 2] - b.lo[2];
+    atomicOr(b.bitmap + ((size_t)(q2 * b.n[1] + q1) * b.wx + (q0 >> 5)), 1u << (q0 & 31));
+    const unsigned long long L = b.slack_bits + ((unsigned long long)((q2 + 1) * (b.n[1] + 2) + (q1 + 1)) << b.row_log2) + (unsigned long long)(q0 + 1);
+    atomicOr(b.pad + (L >> 5), 1u << (L & 31));
+    const int q[3] = {q0, q1, q2};
+    int cl[3], ch[3];
+    for (int a = 0; a < 3; a++) {
+        cl[a] = max(0, (q[a] - 1) / kCoarse);
+        ch[a] = min(b.nc[a] - 1, (q[a] + 1) / kCoarse);
+    }
+    for (int K = cl[2]; K <= ch[2]; K++)
+        for (int J = cl[1]; J <= ch[1]; J++)
+            for (int I = cl[0]; I <= ch[0]; I++) {
+                const uint32_t c = (uint32_t)((K * b.nc[1] + J) * b.nc[0] + I);
+                atomicOr(b.coarse + (c >> 5), 1u << (c & 31));
+            }
+}
+
+// the fully-set one-voxel shell of the padded bitmap: one thread per padded row
+__global__ void __launch_bounds__(256) map_shell_kernel(MapBuild b) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n1p = (uint32_t)b.n[1] + 2, n2p = (uint32_t)b.n[2] + 2;
+    if (row >= n1p * n2p) return;
+    const uint32_t c1 = row % n1p, c2 = row / n1p;
+    const unsigned long long L0 = b.slack_bits + ((unsigned long long)row << b.row_log2);  // multiple of 32
+    uint32_t* w = b.pad + (L0 >> 5);
+    const uint32_t last = (uint32_t)b.n[0] + 1;  // padded x of the far shell cell
+    if (c1 == 0 || c1 == n1p - 1 || c2 == 0 || c2 == n2p - 1) {
+        for (uint32_t x = 0; x <= last; x += 32) {
+            const uint32_t cnt = min(32u, last + 1 - x);
+            atomicOr(w + (x >> 5), cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u));
+        }
+    } else {
+        atomicOr(w, 1u);
+        atomicOr(w + (last >> 5), 1u << (last & 31));
+    }
+}
+
+// exclusive popcount prefix over the occupancy words: one block, each thread a contiguous run
+__global__ void __launch_bounds__(1024) map_prefix_kernel(MapBuild b) {
+    __shared__ uint32_t s_warp[32];
+    const unsigned long long per = (b.nwords + blockDim.x - 1) / blockDim.x;
+    const unsigned long long beg = min(b.nwords, threadIdx.x * per), end = min(b.nwords, beg + per);
+    uint32_t sum = 0;
+    for (unsigned long long w = beg; w < end; w++) sum += __popc(b.bitmap[w]);
+    uint32_t incl = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = s_warp[lane], iv = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, iv, o);
+            if (lane >= o) iv += t;
+        }
+        s_warp[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + incl - sum;
+    for (unsigned long long w = beg; w < end; w++) {
+        b.prefix[w] = run;
+        run += __popc(b.bitmap[w]);
+    }
+}
+
+// raster rank -> leaf rank
+__global__ void __launch_bounds__(256) map_rank_kernel(MapBuild b) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n_occ) return;
+    const int q0 = b.keys[3 * i] - b.lo[0], q1 = b.keys[3 * i + 1] - b.lo[1], q2 = b.keys[3 * i + 2] - b.lo[2];
+    const size_t w = (size_t)(q2 * b.n[1] + q1) * b.wx + (q0 >> 5);
+    b.leaf_of_raster[b.prefix[w] + __popc(b.bitmap[w] & ((1u << (q0 & 31)) - 1u))] = i;
 }
 
 // coverage_count[v] = popcount(vis[v])
@@ -1290,79 +1405,59 @@ int prv_set_map(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, uint32_t
     const int wx = (n[0] + 31) / 32;
     const size_t nwords = (size_t)wx * n[1] * n[2];
     if (nwords > ((size_t)1 << 31)) return fail(ctx, PRV_ERR_UNSUPPORTED, "prv_set_map: occupancy AABB %dx%dx%d too large for a dense bitmap", n[0], n[1], n[2]);
-    std::vector<uint32_t> bitmap(nwords, 0u), prefix(nwords, 0u), leaf_of_raster(N, 0u);
-    auto word_of = [&](const uint16_t* k) { return ((size_t)(k[2] - lo[2]) * n[1] + (size_t)(k[1] - lo[1])) * wx + (size_t)((k[0] - lo[0]) >> 5); };
-    for (uint32_t i = 0; i < N; i++) bitmap[word_of(keys + 3 * i)] |= 1u << ((keys[3 * i] - lo[0]) & 31);
-    uint32_t run = 0;
-    for (size_t w = 0; w < nwords; w++) {
-        prefix[w] = run;
-        run += (uint32_t)__builtin_popcount(bitmap[w]);
-    }
-    for (uint32_t i = 0; i < N; i++) {
-        const size_t w = word_of(keys + 3 * i);
-        const uint32_t bit = (keys[3 * i] - lo[0]) & 31;
-        leaf_of_raster[prefix[w] + (uint32_t)__builtin_popcount(bitmap[w] & ((1u << bit) - 1u))] = i;
-    }
-    // shell-padded bitmap for the branch-free in-AABB march
+    // shell-padded bitmap geometry (branch-free in-AABB march): rows padded to a power of two, 3 planes (+1 row) of
+    // slack on both sides because the 4-deep speculative march may step up to 3 cells past the shell
     int row_log2 = 5;
     while ((1 << row_log2) < n[0] + 2) row_log2++;
     const size_t pad_rows = (size_t)(n[1] + 2) * (n[2] + 2);
-    // slack of 3 planes (+1 row) on both sides: the 4-deep speculative march may step up to 3 cells past the shell
     const size_t slack_bits = ((size_t)3 * (n[1] + 2) + 2) << row_log2;
     const size_t pad_words = ((pad_rows << row_log2) + 2 * slack_bits) / 32;
     if ((pad_rows << row_log2) + 2 * slack_bits >= ((size_t)1 << 31)) return fail(ctx, PRV_ERR_UNSUPPORTED, "prv_set_map: occupancy AABB too large for the padded bitmap");
-    std::vector<uint32_t> pad(pad_words, 0u);
-    auto pad_set = [&](int c0, int c1, int c2) {  // padded coordinates
-        const size_t L = slack_bits + ((((size_t)c2 * (n[1] + 2)) + (size_t)c1) << row_log2) + (size_t)c0;
-        pad[L >> 5] |= 1u << (L & 31);
-    };
-    for (int c2 = 0; c2 < n[2] + 2; c2++)
-        for (int c1 = 0; c1 < n[1] + 2; c1++) {
-            const bool shell_row = c2 == 0 || c2 == n[2] + 1 || c1 == 0 || c1 == n[1] + 1;
-            if (shell_row) {
-                for (int c0 = 0; c0 < n[0] + 2; c0++) pad_set(c0, c1, c2);
-            } else {
-                pad_set(0, c1, c2);
-                pad_set(n[0] + 1, c1, c2);
-            }
-        }
-    for (uint32_t i = 0; i < N; i++) pad_set(keys[3 * i] - lo[0] + 1, keys[3 * i + 1] - lo[1] + 1, keys[3 * i + 2] - lo[2] + 1);
-    // coarse occupancy (cells of kCoarse voxels) dilated by one voxel, for the conservative brick cull
     int nc[3];
     for (int a = 0; a < 3; a++) nc[a] = (n[a] + kCoarse - 1) / kCoarse;
-    std::vector<uint32_t> coarse(((size_t)nc[0] * nc[1] * nc[2] + 31) / 32 + 1, 0u);
-    for (uint32_t i = 0; i < N; i++) {
-        int cl[3], ch[3];
-        for (int a = 0; a < 3; a++) {
-            const int v = keys[3 * i + a] - lo[a];
-            cl[a] = std::max(0, (v - 1) / kCoarse);
-            ch[a] = std::min(nc[a] - 1, (v + 1) / kCoarse);
-        }
-        for (int K = cl[2]; K <= ch[2]; K++)
-            for (int J = cl[1]; J <= ch[1]; J++)
-                for (int I = cl[0]; I <= ch[0]; I++) {
-                    const size_t b = ((size_t)K * nc[1] + J) * nc[0] + I;
-                    coarse[b >> 5] |= 1u << (b & 31);
-                }
-    }
+    const size_t coarse_words = ((size_t)nc[0] * nc[1] * nc[2] + 31) / 32 + 1;
     int rc;
-    if ((rc = ensure(ctx, ctx->d_coarse, coarse.size() * 4))) return rc;
-    CU(h2d(ctx, ctx->d_coarse.p, coarse.data(), coarse.size() * 4));
+    if ((rc = ensure(ctx, ctx->d_coarse, coarse_words * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_bitmap_pad, pad_words * 4))) return rc;
-    CU(h2d(ctx, ctx->d_bitmap_pad.p, pad.data(), pad_words * 4));
     if ((rc = ensure(ctx, ctx->d_bitmap, nwords * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_prefix, nwords * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_leaf_of_raster, (size_t)N * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_keys, (size_t)N * 6))) return rc;
     if ((rc = ensure(ctx, ctx->d_rgb, (size_t)N * 3))) return rc;
-    CU(h2d(ctx, ctx->d_bitmap.p, bitmap.data(), nwords * 4));
-    CU(h2d(ctx, ctx->d_prefix.p, prefix.data(), nwords * 4));
-    CU(h2d(ctx, ctx->d_leaf_of_raster.p, leaf_of_raster.data(), (size_t)N * 4));
+    // the only host->device traffic: leaf keys and colours; every table is built by kernels
     CU(h2d(ctx, ctx->d_keys.p, keys, (size_t)N * 6));
     if (rgb)
         CU(h2d(ctx, ctx->d_rgb.p, rgb, (size_t)N * 3));
     else
         CU(cudaMemsetAsync(ctx->d_rgb.p, 0, (size_t)N * 3, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_coarse.p, 0, coarse_words * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_bitmap_pad.p, 0, pad_words * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_bitmap.p, 0, nwords * 4, ctx->stream));
+    {
+        MapBuild mb{};
+        for (int a = 0; a < 3; a++) {
+            mb.lo[a] = lo[a];
+            mb.n[a] = n[a];
+            mb.nc[a] = nc[a];
+        }
+        mb.wx = wx;
+        mb.row_log2 = row_log2;
+        mb.n_occ = N;
+        mb.slack_bits = slack_bits;
+        mb.nwords = nwords;
+        mb.bitmap = ptr<uint32_t>(ctx->d_bitmap);
+        mb.pad = ptr<uint32_t>(ctx->d_bitmap_pad);
+        mb.coarse = ptr<uint32_t>(ctx->d_coarse);
+        mb.prefix = ptr<uint32_t>(ctx->d_prefix);
+        mb.leaf_of_raster = ptr<uint32_t>(ctx->d_leaf_of_raster);
+        mb.keys = ptr<uint16_t>(ctx->d_keys);
+        Span sp(ctx, K_OTHER, 4);
+        map_scatter_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(mb);
+        map_shell_kernel<<<(uint32_t)((pad_rows + 255) / 256), 256, 0, ctx->stream>>>(mb);
+        map_prefix_kernel<<<1, 1024, 0, ctx->stream>>>(mb);
+        map_rank_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(mb);
+    }
+    CU(cudaGetLastError());
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->h_keys.assign(keys, keys + (size_t)N * 3);
     ctx->resolution = resolution;
