@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(256) greedy_iter_kernel(const uint64_t* rows, 
 __global__ void __launch_bounds__(256) greedy_persistent_kernel(const uint64_t* __restrict__ rows, uint32_t words64, uint32_t nrows,
                                                                 const uint32_t* __restrict__ view_ids, const uint32_t* __restrict__ row_of_id,
                                                                 uint32_t first_row, uint32_t first_id, uint32_t max_iter, unsigned long long* best,
-                                                                uint64_t* cov_out, unsigned int* arrive) {
+                                                                uint64_t* cov_out, unsigned int* arrive, int rows_in_smem) {
     extern __shared__ uint64_t s_cov[];
     __shared__ uint32_t s_red[8];
     __shared__ unsigned long long s_best;
@@ -672,10 +672,22 @@ __global__ void __launch_bounds__(256) greedy_persistent_kernel(const uint64_t* 
         if (blockIdx.x == 0 && threadIdx.x == 0) best[0] = ((unsigned long long)t << 32) | (unsigned long long)(0xFFFFFFFFu - first_id);
         __syncthreads();
     }
+    // the block's own rows live in shared memory after the mask (the grid barrier's __threadfence invalidates L1 every
+    // iteration, so rows left in global memory would be re-fetched from L2 each time)
+    ulonglong2* srows = cov2 + half;
+    if (rows_in_smem) {
+        uint32_t slot = 0;
+        for (uint32_t r = blockIdx.x; r < nrows; r += gridDim.x, slot++) {
+            const ulonglong2* rv = reinterpret_cast<const ulonglong2*>(rows + (size_t)r * words64);
+            for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) srows[(size_t)slot * half + w] = rv[w];
+        }
+        __syncthreads();
+    }
     for (uint32_t k = 1; k <= max_iter; k++) {
         unsigned long long local = 0ull;
-        for (uint32_t r = blockIdx.x; r < nrows; r += gridDim.x) {
-            const ulonglong2* rv = reinterpret_cast<const ulonglong2*>(rows + (size_t)r * words64);
+        uint32_t slot = 0;
+        for (uint32_t r = blockIdx.x; r < nrows; r += gridDim.x, slot++) {
+            const ulonglong2* rv = rows_in_smem ? srows + (size_t)slot * half : reinterpret_cast<const ulonglong2*>(rows + (size_t)r * words64);
             uint32_t c = 0;
             for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) {
                 const ulonglong2 v = rv[w];
@@ -1230,26 +1242,40 @@ int greedy_impl(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter) {
     const size_t cov_bytes = (size_t)words * 8;
     if (cov_bytes <= 160 * 1024) {
         // one persistent cooperative kernel
-        if (ctx->occ_greedy_words != words) {
-            CU(cudaFuncSetAttribute(greedy_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cov_bytes));
-            int occ = 0;
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, greedy_persistent_kernel, 256, cov_bytes));
-            ctx->occ_greedy = std::max(1, occ);
-            ctx->occ_greedy_words = words;
+        // grid: 2 (else 1) blocks per SM with the block's rows resident in shared memory next to the mask when that fits
+        // (<= 100 KB per block at 2 blocks/SM, <= 200 KB at 1), else rows stay in global memory
+        uint32_t grid = 1;
+        size_t smem_bytes = cov_bytes;
+        int rows_in_smem = 0;
+        for (int bps = 2; bps >= 1 && !rows_in_smem; bps--) {
+            const uint32_t g = std::max(1u, std::min<uint32_t>(ctx->g_nrows, (uint32_t)(ctx->sm_count * bps)));
+            const uint32_t rpb = (ctx->g_nrows + g - 1) / g;
+            const size_t need = cov_bytes * (1 + (size_t)rpb);
+            if (need <= (size_t)(200 * 1024) / bps) {
+                grid = g;
+                smem_bytes = need;
+                rows_in_smem = 1;
+            }
+        }
+        if (!rows_in_smem) grid = std::max(1u, std::min<uint32_t>(ctx->g_nrows, (uint32_t)(ctx->sm_count * ctx->greedy_blocks_per_sm)));
+        CU(cudaFuncSetAttribute(greedy_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        int occ = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, greedy_persistent_kernel, 256, smem_bytes));
+        if (occ < 1 || (uint64_t)occ * ctx->sm_count < grid) {
+            if (rows_in_smem || occ < 1) return fail(ctx, PRV_ERR_CUDA, "prv_greedy: persistent kernel does not fit (smem %zu, occupancy %d)", smem_bytes, occ);
+            grid = (uint32_t)(occ * ctx->sm_count);
         }
         if ((rc = ensure(ctx, ctx->d_arrive, 4))) return rc;
         CU(cudaMemsetAsync(ctx->d_arrive.p, 0, 4, ctx->stream));
-        uint32_t grid = std::min<uint32_t>(ctx->g_nrows, (uint32_t)(ctx->sm_count * std::min(ctx->occ_greedy, ctx->greedy_blocks_per_sm)));
-        grid = std::max(1u, grid);
         const uint64_t* rows_p = ctx->g_rows;
         uint32_t words_a = words, nrows_a = ctx->g_nrows, first_row_a = first_row, first_id_a = first_view, max_iter_a = max_iter;
         unsigned long long* best_p = ptr<unsigned long long>(ctx->d_best);
         uint64_t* cov_p = ptr<uint64_t>(ctx->d_cov[0]);
         unsigned int* arrive_p = ptr<unsigned int>(ctx->d_arrive);
         void* args[] = {(void*)&rows_p, (void*)&words_a, (void*)&nrows_a, (void*)&ids, (void*)&row_of_id, (void*)&first_row_a, (void*)&first_id_a,
-                        (void*)&max_iter_a, (void*)&best_p, (void*)&cov_p, (void*)&arrive_p};
+                        (void*)&max_iter_a, (void*)&best_p, (void*)&cov_p, (void*)&arrive_p, (void*)&rows_in_smem};
         Span s(ctx, K_GREEDY, 1);
-        CU(cudaLaunchCooperativeKernel((const void*)greedy_persistent_kernel, dim3(grid), dim3(256), args, cov_bytes, ctx->stream));
+        CU(cudaLaunchCooperativeKernel((const void*)greedy_persistent_kernel, dim3(grid), dim3(256), args, smem_bytes, ctx->stream));
         ctx->greedy_persistent = true;
     } else {
         Span s(ctx, K_GREEDY, max_iter + 2);
