@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256) cull_kernel(const CastParams p) {
         const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
         const bool in_grid = px < p.GW && py < p.GH;
         const unsigned long long pid = (unsigned long long)py * p.GW + px;
-        pids[t] = (uint32_t)pid;
+        pids[t] = ((uint32_t)py << 16) | (uint32_t)px;  // queues carry (y,x) packed: no division downstream
         bool active = in_grid && view_ok;
         if (MASKED && active) {
             const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
@@ -295,12 +295,13 @@ __global__ void __launch_bounds__(256) coarse_kernel(const CastParams p) {
     build_chunk_prefix(p.qcount + p.view_base, p.nviews, s_prefix);
     const uint32_t total = s_prefix[p.nviews];
     uint32_t cur_view = 0xFFFFFFFFu;
+    uint32_t vl = 0;
     for (;;) {
         if (threadIdx.x == 0) s_ticket = atomicAdd(p.tickets + 0, 1u);
         __syncthreads();
         const uint32_t g = s_ticket;
         if (g >= total) break;
-        const uint32_t vl = find_view(s_prefix, p.nviews, g);
+        while (s_prefix[vl + 1] <= g) vl++;  // tickets grow monotonically within a block: amortised O(1)
         const uint32_t view = vl + p.view_base;
         if (view != cur_view) {
             __syncthreads();
@@ -314,17 +315,18 @@ __global__ void __launch_bounds__(256) coarse_kernel(const CastParams p) {
         uint32_t pid = 0;
         if (idx < count) {
             pid = p.queue[(size_t)view * p.queue_cap + idx];
+            const int py = (int)(pid >> 16), px = (int)(pid & 0xFFFFu);
             if (!(vc.flags & kViewFastOk)) {
                 keep = true;
             } else {
-                const int py = (int)(pid / (uint32_t)p.GW), px = (int)(pid - (uint32_t)py * (uint32_t)p.GW);
                 float dx, dy, dz;
                 ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
                 keep = !coarse_miss(p.map, vc, dx, dy, dz);
             }
             if (!keep && p.pix_hit) {
-                p.pix_hit[(size_t)view * p.pix_stride + pid] = kNone;
-                if (p.pix_depth) p.pix_depth[(size_t)view * p.pix_stride + pid] = 0.0f;
+                const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
+                p.pix_hit[o] = kNone;
+                if (p.pix_depth) p.pix_depth[o] = 0.0f;
             }
         }
         block_append(keep, pid, p.queue2 + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
@@ -339,13 +341,14 @@ __global__ void __launch_bounds__(256, 5) march_kernel(const CastParams p) {
     const uint32_t total = s_prefix[p.nviews];
     uint32_t cur_view = 0xFFFFFFFFu;
     uint32_t c_probes = 0, c_hits = 0, c_steps = 0;
+    uint32_t vl = 0;
     for (;;) {
         if (threadIdx.x == 0) s_ticket = atomicAdd(p.tickets + 1, 1u);
         __syncthreads();
         const uint32_t g = s_ticket;
         __syncthreads();
         if (g >= total) break;
-        const uint32_t vl = find_view(s_prefix, p.nviews, g);
+        while (s_prefix[vl + 1] <= g) vl++;  // tickets grow monotonically within a block: amortised O(1)
         const uint32_t view = vl + p.view_base;
         if (view != cur_view) {
             if (cur_view != 0xFFFFFFFFu) {  // flush the finished view's counters
@@ -360,8 +363,9 @@ __global__ void __launch_bounds__(256, 5) march_kernel(const CastParams p) {
         const uint32_t count = p.qcount2[view];
         const uint32_t idx = (g - s_prefix[vl]) * 256u + threadIdx.x;
         if (idx < count) {
-            const uint32_t pid = p.queue2[(size_t)view * p.queue_cap + idx];
-            const int py = (int)(pid / (uint32_t)p.GW), px = (int)(pid - (uint32_t)py * (uint32_t)p.GW);
+            const uint32_t packed = p.queue2[(size_t)view * p.queue_cap + idx];
+            const int py = (int)(packed >> 16), px = (int)(packed & 0xFFFFu);
+            const uint32_t pid = (uint32_t)py * (uint32_t)p.GW + (uint32_t)px;
             CastResult res;
             res.rank = kNone;
             res.steps = 0;
@@ -1536,7 +1540,8 @@ int prv_set_camera(prv_ctx* ctx, const prv_intrinsics* intr, double max_range) {
     if (intr->model < 0 || intr->model > 5) return fail(ctx, PRV_ERR_INVALID, "prv_set_camera: unknown distortion model %d", intr->model);
     if (intr->model == 1)
         return fail(ctx, PRV_ERR_UNSUPPORTED, "prv_set_camera: model 1 (MODIFIED_BROWN_CONRADY) cannot be deprojected (reference asserts, Share_Data.hpp:142)");
-    if ((long long)(intr->width + 1) * (intr->height + 1) > (1ll << 31)) return fail(ctx, PRV_ERR_UNSUPPORTED, "prv_set_camera: image too large");
+    if ((long long)(intr->width + 1) * (intr->height + 1) > (1ll << 31) || intr->width >= 65535 || intr->height >= 65535)
+        return fail(ctx, PRV_ERR_UNSUPPORTED, "prv_set_camera: image too large (queues pack pixel coordinates in 16+16 bits)");
     ctx->intr = *intr;
     ctx->cam.W = intr->width;
     ctx->cam.H = intr->height;
