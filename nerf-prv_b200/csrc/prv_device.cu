@@ -134,35 +134,35 @@ __global__ void __launch_bounds__(256) cull_kernel(const CastParams p) {
     const bool fast = (vc.flags & kViewFastOk) != 0;
 
     if (threadIdx.x < 32) {
+        // Region test (warp 0): the region's rays lie inside the pyramid spanned by the four corner rays taken 2 px
+        // outside the region (the pixel->direction map is affine up to the lens distortion, whose deviation inside any
+        // region was verified on the host to stay within that margin).  If all eight corners of the AABB grown by
+        // 2 voxels lie outside one side plane of the pyramid, no ray of the region can touch the AABB.
+        // lane = plane (0..3) * 8 + box corner (0..7): 32 dot products, one ballot.
         bool skip = false;
         if (!MASKED && view_ok && fast && p.cam.region_cull_ok) {
-            const int c = lane & 3;
-            const float cx = (float)((region_x << 5) + ((c & 1) ? 33 : -2));
-            const float cy = (float)((region_y << 5) + ((c & 2) ? 33 : -2));
-            float dx, dy, dz;
-            ray_direction_approx(p.cam, vc, cx, cy, dx, dy, dz);
-            const float rn = rsqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
-            dx *= rn; dy *= rn; dz *= rn;
-            float sx = dx, sy = dy, sz = dz;
-            sx += __shfl_xor_sync(0xFFFFFFFFu, sx, 1); sy += __shfl_xor_sync(0xFFFFFFFFu, sy, 1); sz += __shfl_xor_sync(0xFFFFFFFFu, sz, 1);
-            sx += __shfl_xor_sync(0xFFFFFFFFu, sx, 2); sy += __shfl_xor_sync(0xFFFFFFFFu, sy, 2); sz += __shfl_xor_sync(0xFFFFFFFFu, sz, 2);
-            const float sn = rsqrtf(fmaf(sx, sx, fmaf(sy, sy, sz * sz)));
-            sx *= sn; sy *= sn; sz *= sn;                        // cone axis
-            float cos_t = fmaf(sx, dx, fmaf(sy, dy, sz * dz));   // smallest cosine over the corners = cone half-angle
-            cos_t = fminf(cos_t, __shfl_xor_sync(0xFFFFFFFFu, cos_t, 1));
-            cos_t = fminf(cos_t, __shfl_xor_sync(0xFFFFFFFFu, cos_t, 2));
-            const float wx = p.map.bcen[0] - vc.origin[0], wy = p.map.bcen[1] - vc.origin[1], wz = p.map.bcen[2] - vc.origin[2];
-            const float dist2 = fmaf(wx, wx, fmaf(wy, wy, wz * wz));
-            const float rad = p.map.brad;
-            if (dist2 > rad * rad * 1.01f && cos_t > 0.5f) {
-                const float inv_d = rsqrtf(dist2);
-                const float cos_p = fmaf(sx, wx, fmaf(sy, wy, sz * wz)) * inv_d;  // angle between cone axis and sphere centre
-                const float sin_a = rad * inv_d;                                     // angular radius of the sphere
-                const float cos_a = sqrtf(fmaxf(0.0f, 1.0f - sin_a * sin_a));
-                const float sin_t = sqrtf(fmaxf(0.0f, 1.0f - cos_t * cos_t));
-                const float cos_sum = fmaf(cos_t, cos_a, -sin_t * sin_a);           // cos(theta + alpha), theta+alpha < pi here
-                skip = cos_p < cos_sum - 1.0e-3f;
-            }
+            const int plane = lane >> 3, corner = lane & 7;
+            // pyramid corners counter-clockwise in pixel space: (x0,y0) (x1,y0) (x1,y1) (x0,y1)
+            const float x0 = (float)((region_x << 5) - 2), x1 = (float)((region_x << 5) + 33);
+            const float y0 = (float)((region_y << 5) - 2), y1 = (float)((region_y << 5) + 33);
+            const float ax = (plane == 0 || plane == 3) ? x0 : x1, ay = (plane == 0 || plane == 1) ? y0 : y1;   // corner `plane`
+            const float bx = (plane == 0 || plane == 1) ? x1 : x0, by = (plane == 1 || plane == 2) ? y1 : y0;   // corner `plane+1`
+            float adx, ady, adz, bdx, bdy, bdz, cdx, cdy, cdz;
+            ray_direction_approx(p.cam, vc, ax, ay, adx, ady, adz);
+            ray_direction_approx(p.cam, vc, bx, by, bdx, bdy, bdz);
+            ray_direction_approx(p.cam, vc, 0.5f * (x0 + x1), 0.5f * (y0 + y1), cdx, cdy, cdz);  // interior reference ray
+            // plane through the origin containing corner rays a and b; orient the normal away from the interior ray
+            float nx = ady * bdz - adz * bdy, ny = adz * bdx - adx * bdz, nz = adx * bdy - ady * bdx;
+            const float sgn = (nx * cdx + ny * cdy + nz * cdz) > 0.0f ? -1.0f : 1.0f;
+            nx *= sgn; ny *= sgn; nz *= sgn;
+            const float inv_n = rsqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
+            const float px = ((corner & 1) ? p.map.bmax[0] : p.map.bmin[0]) - vc.origin[0];
+            const float py = ((corner & 2) ? p.map.bmax[1] : p.map.bmin[1]) - vc.origin[1];
+            const float pz = ((corner & 4) ? p.map.bmax[2] : p.map.bmin[2]) - vc.origin[2];
+            const float dist = fmaf(nx, px, fmaf(ny, py, nz * pz)) * inv_n;  // signed distance of the box corner to the plane
+            const bool outside = dist > 1.0e-5f;                             // float error here is ~1e-7 m
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, outside);
+            skip = ((bal & 0xFFu) == 0xFFu) || ((bal & 0xFF00u) == 0xFF00u) || ((bal & 0xFF0000u) == 0xFF0000u) || ((bal & 0xFF000000u) == 0xFF000000u);
         }
         if (lane == 0) s_skip = skip ? 1 : 0;
     }
@@ -858,6 +858,7 @@ struct prv_ctx {
     bool have_cam = false;
     DevCam cam{};
     prv_intrinsics intr{};
+    prv_intrinsics intr_checked{};  // intrinsics the region-cull validation was last run for
 
     // views
     uint32_t V = 0;
@@ -1555,14 +1556,53 @@ int prv_set_camera(prv_ctx* ctx, const prv_intrinsics* intr, double max_range) {
     ctx->cam.max_range_sq = max_range * max_range;
     ctx->cam.inv_fx = 1.0f / intr->fx;
     ctx->cam.inv_fy = 1.0f / intr->fy;
-    {
-        // region-level cone test needs the pixel->direction map to be close to projective: mild distortion over the image
-        const float xm = std::max(std::fabs((0.0f - intr->ppx) / intr->fx), std::fabs(((float)intr->width - intr->ppx) / intr->fx));
-        const float ym = std::max(std::fabs((0.0f - intr->ppy) / intr->fy), std::fabs(((float)intr->height - intr->ppy) / intr->fy));
-        const float r2 = xm * xm + ym * ym;
-        const float dist = std::fabs(intr->coeffs[0]) * r2 + std::fabs(intr->coeffs[1]) * r2 * r2 + std::fabs(intr->coeffs[4]) * r2 * r2 * r2 +
-                           3.0f * (std::fabs(intr->coeffs[2]) + std::fabs(intr->coeffs[3])) * std::sqrt(r2);
-        ctx->cam.region_cull_ok = (intr->model != 2 || dist < 0.25f) && r2 < 4.0f;
+    const bool same_intr = ctx->have_cam && std::memcmp(&ctx->intr_checked, intr, sizeof(prv_intrinsics)) == 0;
+    if (!same_intr) {
+        // The region-level cull assumes that every pixel of a 32x32 region maps (in normalised image coordinates, the
+        // deprojection of Share_Data.hpp:140-196) inside the quad of the region's corners pushed 2 px outwards.  Exact for
+        // pin-hole models; for the Brown-Conrady polynomial it is checked here for every region of the image on a 9x9 grid
+        // of sample pixels: each must lie inside that quad with at least half a pixel to spare.
+        auto deproject = [&](float pu, float pv, float& x, float& y) {
+            x = (pu - intr->ppx) / intr->fx;
+            y = (pv - intr->ppy) / intr->fy;
+            if (intr->model == 2) {
+                const float r2 = x * x + y * y;
+                const float f = 1 + intr->coeffs[0] * r2 + intr->coeffs[1] * r2 * r2 + intr->coeffs[4] * r2 * r2 * r2;
+                const float ux = x * f + 2 * intr->coeffs[2] * x * y + intr->coeffs[3] * (r2 + 2 * x * x);
+                const float uy = y * f + 2 * intr->coeffs[3] * x * y + intr->coeffs[2] * (r2 + 2 * y * y);
+                x = ux;
+                y = uy;
+            }
+        };
+        bool ok = true;
+        const float spare = 0.5f / std::max(intr->fx, intr->fy);
+        for (int ry = 0; ry * 32 < intr->height + 1 && ok; ry++)
+            for (int rx = 0; rx * 32 < intr->width + 1 && ok; rx++) {
+                float qx[4], qy[4];
+                const float x0 = (float)(rx * 32 - 2), x1 = (float)(rx * 32 + 33), y0 = (float)(ry * 32 - 2), y1 = (float)(ry * 32 + 33);
+                deproject(x0, y0, qx[0], qy[0]);
+                deproject(x1, y0, qx[1], qy[1]);
+                deproject(x1, y1, qx[2], qy[2]);
+                deproject(x0, y1, qx[3], qy[3]);
+                float cx, cy;
+                deproject(0.5f * (x0 + x1), 0.5f * (y0 + y1), cx, cy);
+                for (int sy = 0; sy <= 8 && ok; sy++)
+                    for (int sx = 0; sx <= 8 && ok; sx++) {
+                        float px, py;
+                        deproject((float)(rx * 32) + 31.0f * sx / 8.0f, (float)(ry * 32) + 31.0f * sy / 8.0f, px, py);
+                        for (int e = 0; e < 4; e++) {
+                            const float ex = qx[(e + 1) & 3] - qx[e], ey = qy[(e + 1) & 3] - qy[e];
+                            const float len = std::sqrt(ex * ex + ey * ey);
+                            if (!(len > 0)) { ok = false; break; }
+                            const float side_p = (ex * (py - qy[e]) - ey * (px - qx[e])) / len;
+                            const float side_c = (ex * (cy - qy[e]) - ey * (cx - qx[e])) / len;
+                            // the sample must be on the same side of the edge as the region centre, at least `spare` inside
+                            if (!(side_c != 0 && side_p * (side_c > 0 ? 1.0f : -1.0f) > spare)) { ok = false; break; }
+                        }
+                    }
+            }
+        ctx->cam.region_cull_ok = ok ? 1 : 0;
+        ctx->intr_checked = *intr;
     }
     ctx->have_cam = true;
     ctx->V = 0;  // per-view fast-path proofs depend on max_range
