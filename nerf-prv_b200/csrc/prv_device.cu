@@ -1,5 +1,6 @@
 // prv_device.cu -- device side of include/prv.h: context, HBM layout, kernel launches, NCCL glue.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -Xcompiler -ffp-contract=off (see build.py).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdint.h>
@@ -248,14 +249,15 @@ __global__ void __launch_bounds__(256) cull_kernel(const CastParams p) {
     }
 }
 
-// exclusive prefix of 256-ray chunk counts over the views of this launch -> s_prefix[0..nviews]
+// exclusive prefix of chunk counts (chunk = blockDim.x rays) over the views of this launch -> s_prefix[0..nviews]
 __device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint32_t nviews, uint32_t* s_prefix) {
+    const uint32_t chunk = blockDim.x;
     __shared__ uint32_t s_part[8];
     // each thread owns a contiguous run of views
     const uint32_t per = (nviews + blockDim.x - 1) / blockDim.x;
     const uint32_t b = threadIdx.x * per, e = min(nviews, b + per);
     uint32_t sum = 0;
-    for (uint32_t v = b; v < e; v++) sum += (counts[v] + 255u) >> 8;
+    for (uint32_t v = b; v < e; v++) sum += (counts[v] + chunk - 1u) / chunk;
     // block exclusive scan of the per-thread sums
     uint32_t incl = sum;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -270,7 +272,7 @@ __device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint3
     uint32_t run = woff + incl - sum;
     for (uint32_t v = b; v < e; v++) {
         s_prefix[v] = run;
-        run += (counts[v] + 255u) >> 8;
+        run += (counts[v] + chunk - 1u) / chunk;
     }
     if (threadIdx.x == blockDim.x - 1) s_prefix[nviews] = woff + incl;
     __syncthreads();
@@ -333,7 +335,8 @@ __global__ void __launch_bounds__(256) coarse_kernel(const CastParams p) {
     }
 }
 
-__global__ void __launch_bounds__(256, 5) march_kernel(const CastParams p) {
+template <int BS, int MINB>
+__global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
     __shared__ ViewConst s_vc;
     __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
     __shared__ uint32_t s_ticket;
@@ -361,7 +364,7 @@ __global__ void __launch_bounds__(256, 5) march_kernel(const CastParams p) {
         }
         const ViewConst& vc = s_vc;
         const uint32_t count = p.qcount2[view];
-        const uint32_t idx = (g - s_prefix[vl]) * 256u + threadIdx.x;
+        const uint32_t idx = (g - s_prefix[vl]) * (uint32_t)BS + threadIdx.x;
         if (idx < count) {
             const uint32_t packed = p.queue2[(size_t)view * p.queue_cap + idx];
             const int py = (int)(packed >> 16), px = (int)(packed & 0xFFFFu);
@@ -736,6 +739,95 @@ __global__ void __launch_bounds__(256) greedy_persistent_kernel(const uint64_t* 
     }
 }
 
+// Greedy loop inside ONE thread-block cluster: the whole coverage table lives in the distributed shared memory of the
+// cluster's CTAs (row r -> CTA r mod C, slot r div C), every CTA keeps its own copy of the covered mask.  One iteration =
+// score own rows from shared memory, post the CTA's best to CTA 0 through DSMEM, ONE hardware cluster barrier, every CTA
+// reduces the C candidates itself and ORs the winner's row (read through DSMEM from its owner) into its mask.  No global
+// atomics, no polling; candidates are double-buffered so one barrier per iteration suffices.
+__global__ void __launch_bounds__(512) greedy_cluster_kernel(const uint64_t* __restrict__ rows, uint32_t words64, uint32_t nrows,
+                                                             const uint32_t* __restrict__ view_ids, const uint32_t* __restrict__ row_of_id,
+                                                             uint32_t first_row, uint32_t first_id, uint32_t max_iter, uint32_t rows_per_cta,
+                                                             unsigned long long* best, uint64_t* cov_out) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t rank = cluster.block_rank(), C = cluster.num_blocks();
+    extern __shared__ uint64_t s_mem[];
+    __shared__ unsigned long long s_cand[2][16];
+    __shared__ uint32_t s_red[16];
+    __shared__ unsigned long long s_local;
+    const uint32_t half = words64 / 2;
+    ulonglong2* cov2 = reinterpret_cast<ulonglong2*>(s_mem);
+    ulonglong2* srows = cov2 + half;
+    // own rows -> shared memory; covered = row[first_row]
+    uint32_t nown = 0;
+    for (uint32_t r = rank; r < nrows; r += C, nown++) {
+        const ulonglong2* rv = reinterpret_cast<const ulonglong2*>(rows + (size_t)r * words64);
+        for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) srows[(size_t)nown * half + w] = rv[w];
+    }
+    {
+        const ulonglong2* r0 = reinterpret_cast<const ulonglong2*>(rows + (size_t)first_row * words64);
+        uint32_t c = 0;
+        for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) {
+            const ulonglong2 v = r0[w];
+            cov2[w] = v;
+            c += __popcll(v.x) + __popcll(v.y);
+        }
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, o);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (rank == 0 && threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (uint32_t w = 0; w < (blockDim.x >> 5); w++) t += s_red[w];
+            best[0] = ((unsigned long long)t << 32) | (unsigned long long)(0xFFFFFFFFu - first_id);
+        }
+    }
+    cluster.sync();  // every CTA's rows are resident before anybody reads them remotely
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+    for (uint32_t k = 1; k <= max_iter; k++) {
+        // score own rows: one warp per row
+        if (threadIdx.x == 0) s_local = 0ull;
+        __syncthreads();
+        for (uint32_t slot = warp; slot < nown; slot += nwarp) {
+            const ulonglong2* rv = srows + (size_t)slot * half;
+            uint32_t c = 0;
+            for (uint32_t w = lane; w < half; w += 32) {
+                const ulonglong2 v = rv[w];
+                const ulonglong2 cv = cov2[w];
+                c += __popcll(v.x & ~cv.x) + __popcll(v.y & ~cv.y);
+            }
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, o);
+            if (lane == 0) atomicMax(&s_local, ((unsigned long long)c << 32) | (unsigned long long)(0xFFFFFFFFu - view_ids[rank + slot * C]));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *cluster.map_shared_rank(&s_cand[k & 1][rank], 0) = s_local;
+        cluster.sync();
+        // every CTA reduces the candidates posted at CTA 0
+        unsigned long long b = 0ull;
+        {
+            const unsigned long long* cand0 = cluster.map_shared_rank(&s_cand[k & 1][0], 0);
+            for (uint32_t c = 0; c < C; c++) {
+                const unsigned long long v = cand0[c];
+                b = v > b ? v : b;
+            }
+        }
+        if (rank == 0 && threadIdx.x == 0) best[k] = b;
+        if ((b >> 32) == 0ull) break;  // uniform across the cluster
+        const uint32_t rb = row_of_id[0xFFFFFFFFu - (uint32_t)(b & 0xFFFFFFFFull)];
+        const ulonglong2* rw = cluster.map_shared_rank(srows + (size_t)(rb / C) * half, rb % C);
+        for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) {
+            const ulonglong2 v = rw[w];
+            ulonglong2 cv = cov2[w];
+            cv.x |= v.x;
+            cv.y |= v.y;
+            cov2[w] = cv;
+        }
+        __syncthreads();
+    }
+    cluster.sync();  // nobody exits while its shared memory may still be read remotely
+    if (rank == 0)
+        for (uint32_t w = threadIdx.x; w < words64; w += blockDim.x) cov_out[w] = s_mem[w];
+}
+
 // splat z-buffer -------------------------------------------------------------------------------------
 // Stage 1: one 64-bit atomicMin per point on the CORNER cell of its footprint; stage 2 takes the min over the
 // point_size x point_size corner cells that cover a pixel.  min is associative, so this equals point_size^2 atomics
@@ -840,8 +932,12 @@ struct prv_ctx {
     std::string err;
     int variant = PRV_VARIANT_AXIS;
     int occ_coarse = 0, occ_march = 0, occ_greedy = 0;
+    int march_bs = 64;  // measured: 64 > 128 > 256 by 2-4 % (less time behind the slowest warp of a chunk)
     uint32_t occ_greedy_words = 0;
     bool greedy_persistent = false;
+    // The cluster/DSMEM greedy is correct but measured slower than the grid-barrier kernel on B200 (C2 0.25 vs 0.21 ms,
+    // C3 0.43 vs 0.20 ms): it stays selectable (PRV_GREEDY_CLUSTER=1, exercised by the tests) but is not the default.
+    bool greedy_no_cluster = true;
     int greedy_blocks_per_sm = 2;
     DevBuf d_arrive;
 
@@ -1190,7 +1286,13 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
             p.tickets = ptr<uint32_t>(ctx->d_tickets) + 2 * li;
             if (ctx->occ_coarse == 0) {  // persistent grids = exactly one resident wave
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_coarse, coarse_kernel, 256, 0);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march, march_kernel, 256, 0);
+                if (const char* e = getenv("PRV_MARCH_BS")) ctx->march_bs = atoi(e);
+                if (ctx->march_bs == 128)
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march, march_kernel<128, 10>, 128, 0);
+                else if (ctx->march_bs == 64)
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march, march_kernel<64, 20>, 64, 0);
+                else
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march, march_kernel<256, 5>, 256, 0);
                 ctx->occ_coarse = std::max(1, ctx->occ_coarse);
                 ctx->occ_march = std::max(1, ctx->occ_march);
             }
@@ -1204,7 +1306,12 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
                 coarse_kernel<<<(uint32_t)(ctx->sm_count * ctx->occ_coarse), 256, 0, ctx->stream>>>(p);
             }
             Span s(ctx, K_MARCH, 1);
-            march_kernel<<<(uint32_t)(ctx->sm_count * ctx->occ_march), 256, 0, ctx->stream>>>(p);
+            if (ctx->march_bs == 128)
+                march_kernel<128, 10><<<(uint32_t)(ctx->sm_count * ctx->occ_march), 128, 0, ctx->stream>>>(p);
+            else if (ctx->march_bs == 64)
+                march_kernel<64, 20><<<(uint32_t)(ctx->sm_count * ctx->occ_march), 64, 0, ctx->stream>>>(p);
+            else
+                march_kernel<256, 5><<<(uint32_t)(ctx->sm_count * ctx->occ_march), 256, 0, ctx->stream>>>(p);
         } else {
             Span s(ctx, K_CAST, 1);
             if (ctx->variant == PRV_VARIANT_PLAIN)
@@ -1245,7 +1352,46 @@ int greedy_impl(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter) {
     const uint32_t first_row = ctx->h_row_of_id[first_view];
     if (first_row == kNone) return fail(ctx, PRV_ERR_INVALID, "prv_greedy: first_view %u is not a resident view id", first_view);
     const size_t cov_bytes = (size_t)words * 8;
-    if (cov_bytes <= 160 * 1024) {
+    // 1st choice: one thread-block cluster holding the whole table in distributed shared memory
+    bool launched = false;
+    if (!ctx->greedy_no_cluster) {
+        for (uint32_t C = 8; C <= 16 && !launched; C *= 2) {
+            const uint32_t rpc = (ctx->g_nrows + C - 1) / C;
+            const size_t smem = cov_bytes * (1 + (size_t)rpc);
+            if (smem > (size_t)220 * 1024) continue;
+            if (cudaFuncSetAttribute(greedy_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) break;
+            if (C > 8 && cudaFuncSetAttribute(greedy_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) break;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(C);
+            cfg.blockDim = dim3(512);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = ctx->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = C;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, greedy_cluster_kernel, &cfg) != cudaSuccess || nclusters < 1) {
+                cudaGetLastError();
+                continue;
+            }
+            Span s(ctx, K_GREEDY, 1);
+            const cudaError_t e = cudaLaunchKernelEx(&cfg, greedy_cluster_kernel, ctx->g_rows, words, ctx->g_nrows, ids, row_of_id, first_row, first_view,
+                                                     max_iter, rpc, ptr<unsigned long long>(ctx->d_best), ptr<uint64_t>(ctx->d_cov[0]));
+            if (e == cudaSuccess) {
+                launched = true;
+                ctx->greedy_persistent = true;
+            } else {
+                cudaGetLastError();
+            }
+        }
+    }
+    if (launched) {
+        // done
+    } else if (cov_bytes <= 160 * 1024) {
         // one persistent cooperative kernel
         // grid: 2 (else 1) blocks per SM with the block's rows resident in shared memory next to the mask when that fits
         // (<= 100 KB per block at 2 blocks/SM, <= 200 KB at 1), else rows stay in global memory
@@ -1368,6 +1514,7 @@ int prv_create(prv_ctx** out, int device) {
         return fail(nullptr, PRV_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     for (auto& s : ctx->slots) cudaEventCreate(&s);
+    if (const char* e = getenv("PRV_GREEDY_CLUSTER")) ctx->greedy_no_cluster = atoi(e) == 0;
     *out = ctx;
     return PRV_OK;
 }

@@ -221,3 +221,23 @@ def test_full_size_properties_C1(prv, synth, ctx):
     assert st["rays"] == 32 * 640 * 480
     seq, gain = ctx.greedy(0, 64)
     assert len(set(seq.tolist())) == len(seq) and gain[1:].tolist() == sorted(gain[1:].tolist(), reverse=True)
+
+
+def test_greedy_grid_barrier_path_matches_cluster_path(prv, orc, synth, monkeypatch):
+    """The greedy has two implementations (one thread-block cluster with the table in distributed shared memory; a
+    persistent grid-barrier kernel for tables that do not fit): both must give the oracle's sequence."""
+    w = small_workload(prv, synth, "C2", 100, (96, 72))
+    results = []
+    for use_cluster in ("0", "1"):
+        monkeypatch.setenv("PRV_GREEDY_CLUSTER", use_cluster)
+        c = prv.Context(0)
+        c.set_map(w["keys"], w["map_rgb"], w["resolution"])
+        c.set_camera(w["intr"], 1.0)
+        bits, _, _, _ = c.cast_views(w["pose_world"], w["init_pos"], mode=prv.MODE_DENSE)
+        c.greedy_async(5, 64)
+        seq, gain, cov = c.get_greedy(64)
+        o_seq, o_gain, o_cov, _ = orc.greedy(bits, 5, 64)
+        assert seq.tolist() == o_seq.tolist() and gain.tolist() == o_gain.tolist() and np.array_equal(cov, o_cov)
+        results.append(seq.tolist())
+        c.close()
+    assert results[0] == results[1]
