@@ -1,0 +1,175 @@
+"""Edge cases of the CUDA path against the oracle: odd image sizes, pin-hole / Brown-Conrady(4) cameras, camera inside
+the occupancy AABB, thin and single-voxel maps, coarse voxels, unlimited range, more views than one launch batch, and
+the error behaviour of the C ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_rows(orc, keys, rgb, res, intr, pose_world, init_pos, max_range=1.0):
+    m = orc.Map.from_keys(keys, rgb, res)
+    it = orc.make_intrinsics(intr.width, intr.height, intr.fx, intr.fy, intr.ppx, intr.ppy, intr.model, list(intr.coeffs))
+    words = orc.bitset_words(m.n)
+    hits, rows = [], []
+    for v in range(len(init_pos)):
+        ok, r, d = m.cast_view_dense(it, pose_world[v], init_pos[v], max_range=max_range, want_depth=False)
+        hits.append(r)
+        rows.append(orc.bitset_from_ranks(r, words))
+    return m, it, np.stack(hits), np.stack(rows)
+
+
+def check_dense(prv, orc, ctx, keys, rgb, res, intr, pose_world, init_pos, max_range=1.0, variants=(0, 1, 2)):
+    m, it, o_hit, o_rows = oracle_rows(orc, keys, rgb, res, intr, pose_world, init_pos, max_range)
+    for variant in variants:
+        ctx.set_variant(variant)
+        ctx.set_map(keys, rgb, res)
+        ctx.set_camera(intr, max_range)
+        bits, counts, hit, _ = ctx.cast_views(pose_world, init_pos, mode=prv.MODE_DENSE, want_hit_rank=True)
+        assert np.array_equal(hit, o_hit), "variant %d" % variant
+        assert np.array_equal(bits, o_rows)
+    ctx.set_variant(2)
+    return o_hit
+
+
+@pytest.mark.parametrize("size", [(97, 61), (33, 9), (31, 7), (257, 130)])
+def test_odd_image_sizes(prv, orc, synth, ctx, size):
+    w = synth.build_workload(prv, "C1", n_views=3, size=size)
+    hit = check_dense(prv, orc, ctx, w["keys"], w["map_rgb"], w["resolution"], w["intr"], w["pose_world"], w["init_pos"])
+    assert (hit != orc.NONE).sum() > 10
+
+
+@pytest.mark.parametrize("model", [0, 4])
+def test_pinhole_camera_models(prv, orc, synth, ctx, model):
+    w = synth.build_workload(prv, "C1", n_views=3, size=(128, 96))
+    it = w["intr"]
+    intr = prv.make_intrinsics(it.width, it.height, it.fx, it.fy, it.ppx, it.ppy, model, list(it.coeffs))
+    check_dense(prv, orc, ctx, w["keys"], w["map_rgb"], w["resolution"], intr, w["pose_world"], w["init_pos"])
+    # voxel mode too (projection without distortion)
+    m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
+    oit = orc.make_intrinsics(it.width, it.height, it.fx, it.fy, it.ppx, it.ppy, model, list(it.coeffs))
+    bits, counts, hit, _ = ctx.cast_views(w["pose_world"], w["init_pos"], mode=prv.MODE_VOXEL, want_hit_rank=True)
+    for v in range(3):
+        ok, pts, ranks = m.precept(oit, w["pose_world"][v], w["init_pos"][v])
+        assert np.array_equal(hit[v], ranks)
+
+
+def test_strong_distortion_disables_region_cull_but_stays_exact(prv, orc, synth, ctx):
+    w = synth.build_workload(prv, "C1", n_views=2, size=(160, 120))
+    it = w["intr"]
+    intr = prv.make_intrinsics(it.width, it.height, it.fx, it.fy, it.ppx, it.ppy, 2, (0.9, -1.5, 0.05, -0.04, 0.8))
+    check_dense(prv, orc, ctx, w["keys"], w["map_rgb"], w["resolution"], intr, w["pose_world"], w["init_pos"], variants=(1, 2))
+
+
+def test_camera_inside_the_aabb(prv, orc, synth, ctx):
+    """view_space_radius smaller than the object: the origin key lies inside the occupancy AABB (approach phase empty)."""
+    w = synth.build_workload(prv, "C1", n_views=6, size=(96, 72), view_space_radius=0.03)
+    lo, hi = w["keys"].min(0).astype(int), w["keys"].max(0).astype(int)
+    inside = 0
+    for ip in w["init_pos"]:
+        k = np.floor(ip / w["resolution"]).astype(int) + 32768
+        inside += int(np.all(k >= lo) and np.all(k <= hi))
+    assert inside >= 3
+    hit = check_dense(prv, orc, ctx, w["keys"], w["map_rgb"], w["resolution"], w["intr"], w["pose_world"], w["init_pos"])
+    assert (hit != orc.NONE).sum() > 100
+
+
+def test_single_voxel_and_thin_maps(prv, orc, synth, ctx):
+    w = synth.build_workload(prv, "C1", n_views=4, size=(64, 48))
+    one = np.array([[32768, 32770, 32765]], dtype=np.uint16)
+    hit = check_dense(prv, orc, ctx, one, np.array([[9, 8, 7]], dtype=np.uint8), 0.002, w["intr"], w["pose_world"], w["init_pos"])
+    assert (hit == 0).sum() >= 1 and ctx.full_voxels == 1 and ctx.words == 2
+    # a one-voxel-thick slab, built in leaf order through the host shim
+    xs, ys = np.meshgrid(np.arange(-20, 21), np.arange(-15, 16))
+    pts = np.stack([xs.ravel() * 0.002 + 0.001, ys.ravel() * 0.002 + 0.001, np.full(xs.size, 0.0031)], axis=1).astype(np.float32)
+    keys, rgb = prv.host_build_map(pts, np.full((len(pts), 3), 100, dtype=np.uint8), 0.002)
+    assert len(keys) == 41 * 31 and len(set(keys[:, 2].tolist())) == 1
+    hit = check_dense(prv, orc, ctx, keys, rgb, 0.002, w["intr"], w["pose_world"], w["init_pos"])
+    assert (hit != orc.NONE).sum() > 50
+
+
+def test_coarse_resolution_and_unlimited_range(prv, orc, synth, ctx):
+    w = synth.build_workload(prv, "C1", n_views=3, size=(96, 72))
+    keys, rgb = prv.host_build_map(w["cloud"], w["cloud_rgb"], 0.006)
+    check_dense(prv, orc, ctx, keys, rgb, 0.006, w["intr"], w["pose_world"], w["init_pos"])
+    # maxRange <= 0: castRay has no range limit; the march ends at the hit, the AABB exit or the key-space border
+    check_dense(prv, orc, ctx, w["keys"], w["map_rgb"], w["resolution"], w["intr"], w["pose_world"], w["init_pos"], max_range=0.0, variants=(1, 2))
+
+
+def test_more_views_than_one_launch_batch(prv, orc, synth, ctx):
+    """2100 views > kMaxViewsPerLaunch (2048): the persistent kernels run in two view batches."""
+    w = synth.build_workload(prv, "C1", n_views=100, size=(24, 16))
+    reps = 21
+    pw = np.concatenate([w["pose_world"]] * reps)
+    ip = np.concatenate([w["init_pos"]] * reps)
+    ctx.set_variant(2)
+    ctx.set_map(w["keys"], w["map_rgb"], w["resolution"])
+    ctx.set_camera(w["intr"], 1.0)
+    bits, counts, hit, _ = ctx.cast_views(pw, ip, mode=prv.MODE_DENSE, want_hit_rank=True)
+    m, it, o_hit, o_rows = oracle_rows(orc, w["keys"], w["map_rgb"], w["resolution"], w["intr"], w["pose_world"], w["init_pos"])
+    for r in range(reps):
+        assert np.array_equal(hit[r * 100:(r + 1) * 100], o_hit) and np.array_equal(bits[r * 100:(r + 1) * 100], o_rows)
+    seq, gain = ctx.greedy(2099, 3)
+    o_seq, o_gain, _, _ = orc.greedy(bits, 2099, 3)
+    assert seq.tolist() == o_seq.tolist() and gain.tolist() == o_gain.tolist()
+    seq, gain = ctx.greedy(5, 0)   # max_iter = 0: only the start view
+    assert seq.tolist() == [5] and gain.tolist() == [int(counts[5])]
+
+
+def test_error_behaviour(prv, synth, ctx):
+    L = prv.lib()
+    w = synth.build_workload(prv, "C1", n_views=2, size=(32, 24))
+    c = prv.Context(0)
+    # call order
+    with pytest.raises(prv.PrvError) as e:
+        c.set_views(w["pose_world"], w["init_pos"])
+    assert e.value.code == prv.ERR_INVALID and "prv_set_map" in str(e.value)
+    with pytest.raises(prv.PrvError):
+        c.cast_async(prv.MODE_DENSE)
+    # keys not in leaf order / duplicates
+    bad = w["keys"][::-1].copy()
+    with pytest.raises(prv.PrvError) as e:
+        c.set_map(bad, None, 0.002)
+    assert "leaf (Morton) order" in str(e.value)
+    with pytest.raises(prv.PrvError):
+        c.set_map(np.zeros((0, 3), dtype=np.uint16), None, 0.002)
+    with pytest.raises(prv.PrvError):
+        c.set_map(w["keys"], None, -1.0)
+    c.set_map(w["keys"], None, 0.002)
+    # unsupported / invalid cameras
+    it = w["intr"]
+    for model, code in ((3, prv.ERR_UNSUPPORTED), (5, prv.ERR_UNSUPPORTED), (1, prv.ERR_UNSUPPORTED), (7, prv.ERR_INVALID)):
+        with pytest.raises(prv.PrvError) as e:
+            c.set_camera(prv.make_intrinsics(it.width, it.height, it.fx, it.fy, it.ppx, it.ppy, model), 1.0)
+        assert e.value.code == code
+    with pytest.raises(prv.PrvError):
+        c.set_camera(prv.make_intrinsics(0, 10, 1, 1, 0, 0, 0), 1.0)
+    c.set_camera(it, 1.0)
+    c.set_views(w["pose_world"], w["init_pos"])
+    with pytest.raises(prv.PrvError):
+        c.cast_async(7)
+    with pytest.raises(prv.PrvError):
+        c.greedy_async(0, 4)          # nothing cast yet
+    with pytest.raises(prv.PrvError):
+        c.get_bitsets()
+    c.cast_async(prv.MODE_DENSE, False)
+    with pytest.raises(prv.PrvError):
+        c.get_hit_rank(prv.MODE_DENSE)  # per-pixel results were not kept
+    with pytest.raises(prv.PrvError):
+        c.greedy_async(99, 4)         # not a resident view id
+    with pytest.raises(prv.PrvError):
+        c.render_async(2, 5)          # no cloud
+    with pytest.raises(prv.PrvError):
+        c.set_variant(9)
+    # NULL context never crashes
+    assert L.prv_sync(None) == prv.ERR_INVALID and L.prv_cast_async(None, 1, 0) == prv.ERR_INVALID
+    assert L.prv_set_map(None, None, None, 0, 0.002) == prv.ERR_INVALID
+    h = C.c_void_p()
+    assert L.prv_create(C.byref(h), 4096) == prv.ERR_INVALID and b"out of range" in L.prv_last_error(None)
+    # the context is still usable after errors
+    c.greedy_async(1, 4)
+    seq, gain, _ = c.get_greedy(4)
+    assert seq[0] == 1
+    c.close()
