@@ -178,6 +178,17 @@ int prv_render_views(prv_ctx* ctx, const double* pose_world, uint32_t V, int poi
 int prv_render_async(prv_ctx* ctx, uint32_t V, int point_size); /* resident: uses prv_set_views poses, output stays on device */
 float prv_splat_focal(const prv_intrinsics* intr);
 
+/* ---------------------------------------------------------------- ensemble-uncertainty view scoring
+ * NBV_Net_Labeler::nbv_loop cases 2 (EnsembleRGB) and 3 (EnsembleRGBDensity), main.cpp:2039-2161: per candidate view the
+ * per-pixel variance of `E` ensemble renders is accumulated into one score and the arg-max view is returned (strict '>'
+ * from -1e100, main.cpp:1971,2088,2152; `chosen[i] != 0` skips view i like chosen_nbvs_set, may be NULL).
+ * images: [V][E][H][W][4] uint8 in the channel order cv::imread(IMREAD_UNCHANGED) yields (0..2 colour, 3 alpha).
+ * The per-pixel terms are computed in parallel and summed per view in the reference's pixel order, so method 3 is
+ * bit-exact; method 2 is bit-exact for E == 2 (the value the reference uses, Share_Data.hpp:505-507: log terms come from
+ * a host-computed table), otherwise within 1e-12 relative (CUDA log). */
+int prv_score_ensemble(prv_ctx* ctx, const uint8_t* images, uint32_t V, uint32_t E, int W, int H, int method,
+                       const uint8_t* chosen, double* scores_out /* V */, int32_t* best_view_out);
+
 /* ---------------------------------------------------------------- timing (CUDA events on the ctx stream) */
 int prv_timing_reset(prv_ctx* ctx);
 int prv_get_timing(prv_ctx* ctx, prv_timing* out); /* synchronises */

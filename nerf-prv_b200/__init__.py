@@ -116,6 +116,7 @@ def lib():
         "prv_render_views": (i, [vp, P(d), u32, i, P(u8), P(f)]),
         "prv_render_async": (i, [vp, u32, i]),
         "prv_splat_focal": (f, [P(Intrinsics)]),
+        "prv_score_ensemble": (i, [vp, P(u8), u32, u32, i, i, i, P(u8), P(d), P(C.c_int32)]),
         "prv_timing_reset": (i, [vp]),
         "prv_get_timing": (i, [vp, P(Timing)]),
         "prv_event_record": (i, [vp, i]),
@@ -407,6 +408,16 @@ class Context:
 
     def render_async(self, V, point_size=5):
         self._chk(lib().prv_render_async(self._h, V, point_size))
+
+    def score_ensemble(self, images, method, chosen=None):
+        """nbv_loop cases 2/3: images [V][E][H][W][4] uint8 -> (best view id, scores[V])."""
+        im = np.ascontiguousarray(images, dtype=np.uint8)
+        V, E, H, W, _ = im.shape
+        scores = np.zeros(V)
+        best = C.c_int32(-1)
+        ch = None if chosen is None else np.ascontiguousarray(chosen, dtype=np.uint8)
+        self._chk(lib().prv_score_ensemble(self._h, _p(im, C.c_uint8), V, E, W, H, method, _p(ch, C.c_uint8), _p(scores, C.c_double), C.byref(best)))
+        return best.value, scores
 
     def timing_reset(self):
         self._chk(lib().prv_timing_reset(self._h))

@@ -828,6 +828,73 @@ __global__ void __launch_bounds__(512) greedy_cluster_kernel(const uint64_t* __r
         for (uint32_t w = threadIdx.x; w < words64; w += blockDim.x) cov_out[w] = s_mem[w];
 }
 
+// ensemble-uncertainty scoring (nbv_loop cases 2/3, main.cpp:2039-2161) ------------------------------------------
+// Stage 1: one thread per (view, pixel) computes the pixel's contribution(s) in the reference's double arithmetic.
+// Stage 2: one thread per view adds them in the reference's order (row-major pixels, channel order), so the score is
+// the same sequence of double additions.  NaN marks "no term" (method 2 skips variances <= 1e-10).
+__global__ void __launch_bounds__(256) ensemble_terms_kernel(const uint8_t* __restrict__ images, uint32_t E, uint32_t npix, int method,
+                                                             const double* __restrict__ log_lut, double* __restrict__ terms) {
+    const uint32_t view = blockIdx.y;
+    const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const uchar4* base = reinterpret_cast<const uchar4*>(images) + (size_t)view * E * npix + pix;
+    double mean[3] = {0.0, 0.0, 0.0};
+    double mean_density = 0.0;
+    for (uint32_t e = 0; e < E; e++) {
+        const uchar4 px = base[(size_t)e * npix];
+        mean[0] = prvk::dadd(mean[0], (double)px.x);
+        mean[1] = prvk::dadd(mean[1], (double)px.y);
+        mean[2] = prvk::dadd(mean[2], (double)px.z);
+        mean_density = prvk::dadd(mean_density, prvk::ddiv((double)px.w, 255.0));
+    }
+    for (int c = 0; c < 3; c++) mean[c] = prvk::ddiv(mean[c], (double)E);
+    mean_density = prvk::ddiv(mean_density, (double)E);
+    double variance[3] = {0.0, 0.0, 0.0};
+    for (uint32_t e = 0; e < E; e++) {
+        const uchar4 px = base[(size_t)e * npix];
+        const double v[3] = {(double)px.x, (double)px.y, (double)px.z};
+        for (int c = 0; c < 3; c++) {
+            const double d = prvk::dsub(v[c], mean[c]);
+            variance[c] = prvk::dadd(variance[c], prvk::dmul(d, d));
+        }
+    }
+    for (int c = 0; c < 3; c++) variance[c] = prvk::ddiv(variance[c], (double)E);
+    double* out = terms + ((size_t)view * npix + pix) * 3;
+    const double nan = __longlong_as_double(0x7FF8000000000000ll);
+    if (method == 2) {
+        for (int c = 0; c < 3; c++) {
+            double t = nan;
+            if (variance[c] > 1e-10) {
+                if (log_lut) {  // E == 2: variance = (|a-b|/2)^2 exactly; host libm values
+                    const uchar4 p0 = base[0], p1 = base[npix];
+                    const int a = c == 0 ? p0.x : (c == 1 ? p0.y : p0.z), b = c == 0 ? p1.x : (c == 1 ? p1.y : p1.z);
+                    t = log_lut[a > b ? a - b : b - a];
+                } else {
+                    t = log(variance[c]);
+                }
+            }
+            out[c] = t;
+        }
+    } else {
+        out[0] = prvk::ddiv(prvk::dadd(prvk::dadd(variance[0], variance[1]), variance[2]), 3.0);
+        const double q = prvk::dsub(1.0, mean_density);
+        out[1] = prvk::dmul(q, q);
+        out[2] = nan;
+    }
+}
+
+__global__ void __launch_bounds__(32) ensemble_sum_kernel(const double* __restrict__ terms, uint32_t V, uint32_t npix, double* __restrict__ scores) {
+    const uint32_t view = blockIdx.x * blockDim.x + threadIdx.x;
+    if (view >= V) return;
+    const double* t = terms + (size_t)view * npix * 3;
+    double acc = 0.0;
+    for (size_t i = 0; i < (size_t)npix * 3; i++) {
+        const double v = t[i];
+        if (v == v) acc = prvk::dadd(acc, v);
+    }
+    scores[view] = acc;
+}
+
 // splat z-buffer -------------------------------------------------------------------------------------
 // Stage 1: one 64-bit atomicMin per point on the CORNER cell of its footprint; stage 2 takes the min over the
 // point_size x point_size corner cells that cover a pixel.  min is associative, so this equals point_size^2 atomics
@@ -940,6 +1007,7 @@ struct prv_ctx {
     bool greedy_no_cluster = true;
     int greedy_blocks_per_sm = 2;
     DevBuf d_arrive;
+    DevBuf d_ens_images, d_ens_terms, d_ens_scores;
 
     // map
     bool have_map = false;
@@ -1525,7 +1593,7 @@ void prv_destroy(prv_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     prv_comm_destroy(ctx);
     DevBuf* bufs[] = {&ctx->d_coarse, &ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
-                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_tickets, &ctx->d_arrive, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
+                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_tickets, &ctx->d_arrive, &ctx->d_ens_images, &ctx->d_ens_terms, &ctx->d_ens_scores, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
                       &ctx->d_voxel_pix, &ctx->d_voxel_hit, &ctx->d_points, &ctx->d_best, &ctx->d_cov[0], &ctx->d_cov[1], &ctx->d_all_rows,
                       &ctx->d_all_ids, &ctx->d_cloud_xyz, &ctx->d_cloud_rgb, &ctx->d_corner, &ctx->d_rgba, &ctx->d_depth_img, &ctx->d_flush};
     for (DevBuf* b : bufs) release(*b);
@@ -1983,6 +2051,54 @@ int prv_render_views(prv_ctx* ctx, const double* pose_world, uint32_t V, int poi
     CU(d2h(ctx, rgba_out, ctx->d_rgba.p, px * 4));
     if (depth_out) CU(d2h(ctx, depth_out, ctx->d_depth_img.p, px * 4));
     CU(cudaStreamSynchronize(ctx->stream));
+    return PRV_OK;
+}
+
+int prv_score_ensemble(prv_ctx* ctx, const uint8_t* images, uint32_t V, uint32_t E, int W, int H, int method, const uint8_t* chosen,
+                       double* scores_out, int32_t* best_view_out) {
+    if (!ctx) return PRV_ERR_INVALID;
+    if (!images || V == 0 || E == 0 || W <= 0 || H <= 0 || (method != 2 && method != 3))
+        return fail(ctx, PRV_ERR_INVALID, "prv_score_ensemble: bad arguments (method must be 2 or 3)");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t npix = (uint32_t)W * (uint32_t)H;
+    const size_t img_bytes = (size_t)V * E * npix * 4;
+    int rc;
+    if ((rc = ensure(ctx, ctx->d_ens_images, img_bytes))) return rc;
+    if ((rc = ensure(ctx, ctx->d_ens_terms, (size_t)V * npix * 3 * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->d_ens_scores, (size_t)V * 8 + 256 * 8))) return rc;
+    CU(h2d(ctx, ctx->d_ens_images.p, images, img_bytes));
+    const double* lut = nullptr;
+    double host_lut[256];
+    if (method == 2 && E == 2) {
+        host_lut[0] = 0.0;  // never used: variance 0 is skipped
+        for (int d = 1; d < 256; d++) host_lut[d] = std::log(((double)d * (double)d) / 4.0);  // ((a-m)^2 + (b-m)^2) / 2 with m = (a+b)/2
+        CU(h2d(ctx, ptr<double>(ctx->d_ens_scores) + V, host_lut, sizeof(host_lut)));
+        lut = ptr<double>(ctx->d_ens_scores) + V;
+    }
+    {
+        Span s(ctx, K_OTHER, 2);
+        ensemble_terms_kernel<<<dim3((npix + 255) / 256, V), 256, 0, ctx->stream>>>(ptr<uint8_t>(ctx->d_ens_images), E, npix, method, lut,
+                                                                                  ptr<double>(ctx->d_ens_terms));
+        ensemble_sum_kernel<<<(V + 31) / 32, 32, 0, ctx->stream>>>(ptr<double>(ctx->d_ens_terms), V, npix, ptr<double>(ctx->d_ens_scores));
+    }
+    CU(cudaGetLastError());
+    std::vector<double> scores(V);
+    CU(d2h(ctx, scores.data(), ctx->d_ens_scores.p, (size_t)V * 8));
+    CU(cudaStreamSynchronize(ctx->stream));
+    double largest = -1e100;  // main.cpp:1971
+    int32_t best = -1;
+    for (uint32_t i = 0; i < V; i++) {
+        if (chosen && chosen[i]) {
+            scores[i] = 0.0;
+            continue;
+        }
+        if (scores[i] > largest) {  // strict '>': first maximum wins (main.cpp:2088, :2152)
+            largest = scores[i];
+            best = (int32_t)i;
+        }
+    }
+    if (scores_out) std::memcpy(scores_out, scores.data(), (size_t)V * 8);
+    if (best_view_out) *best_view_out = best;
     return PRV_OK;
 }
 

@@ -97,6 +97,8 @@ def lib():
     L.orc_splat.argtypes = [P(f), P(u8), u64, P(Intrinsics), P(d), C.c_int, P(u8), P(f), P(u32)]
     L.orc_splat_focal.argtypes = [P(Intrinsics)]
     L.orc_splat_focal.restype = f
+    L.orc_score_ensemble.argtypes = [P(u8), u32, u32, C.c_int, C.c_int, C.c_int, P(u8), P(d)]
+    L.orc_score_ensemble.restype = C.c_int
     _lib = L
     return L
 
@@ -291,3 +293,13 @@ def splat(points, rgb, intr, pose_world, point_size=5):
 
 def splat_focal(intr):
     return float(lib().orc_splat_focal(C.byref(intr)))
+
+
+def score_ensemble(images, method, chosen=None):
+    """images: [V][E][H][W][4] uint8 -> (best view id, scores[V])."""
+    im = np.ascontiguousarray(images, dtype=np.uint8)
+    V, E, H, W, _ = im.shape
+    scores = np.zeros(V)
+    ch = None if chosen is None else np.ascontiguousarray(chosen, dtype=np.uint8)
+    best = lib().orc_score_ensemble(_ptr(im, C.c_uint8), V, E, W, H, method, None if ch is None else _ptr(ch, C.c_uint8), _ptr(scores, C.c_double))
+    return best, scores

@@ -855,4 +855,51 @@ void orc_splat(const float* pts, const uint8_t* rgb, uint64_t P, const orc_intri
     }
 }
 
+/* nbv_loop case 2 (main.cpp:2039-2097) and case 3 (:2099-2161), per view; argmax :2088 / :2152 with largest = -1e100 (:1971). */
+int orc_score_ensemble(const uint8_t* images, uint32_t V, uint32_t E, int W, int H, int method, const uint8_t* chosen, double* scores_out) {
+    double largest_view_uncertainty = -1e100;
+    int best_view_id = -1;
+    const size_t img = (size_t)W * H * 4;
+    for (uint32_t i = 0; i < V; i++) {
+        if (scores_out) scores_out[i] = 0.0;
+        if (chosen && chosen[i]) continue;
+        const uint8_t* base = images + (size_t)i * E * img;
+        double view_uncertainty = 0.0;
+        for (int j = 0; j < H; j++) {
+            for (int k = 0; k < W; k++) {
+                double mean[3] = {0.0, 0.0, 0.0};
+                double mean_density = 0.0;
+                for (uint32_t e = 0; e < E; e++) {
+                    const uint8_t* px = base + e * img + ((size_t)j * W + k) * 4;
+                    mean[0] += px[0];
+                    mean[1] += px[1];
+                    mean[2] += px[2];
+                    mean_density += px[3] / 255.0;
+                }
+                for (int c = 0; c < 3; c++) mean[c] /= E;
+                mean_density /= E;
+                double variance[3] = {0.0, 0.0, 0.0};
+                for (uint32_t e = 0; e < E; e++) {
+                    const uint8_t* px = base + e * img + ((size_t)j * W + k) * 4;
+                    for (int c = 0; c < 3; c++) variance[c] += (px[c] - mean[c]) * (px[c] - mean[c]);
+                }
+                for (int c = 0; c < 3; c++) variance[c] /= E;
+                if (method == 2) {
+                    for (int c = 0; c < 3; c++)
+                        if (variance[c] > 1e-10) view_uncertainty += std::log(variance[c]);
+                } else {
+                    view_uncertainty += (variance[0] + variance[1] + variance[2]) / 3.0;
+                    view_uncertainty += (1.0 - mean_density) * (1.0 - mean_density);
+                }
+            }
+        }
+        if (scores_out) scores_out[i] = view_uncertainty;
+        if (view_uncertainty > largest_view_uncertainty) {
+            largest_view_uncertainty = view_uncertainty;
+            best_view_id = (int)i;
+        }
+    }
+    return best_view_id;
+}
+
 }  // extern "C"

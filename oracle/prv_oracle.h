@@ -128,6 +128,13 @@ void orc_splat(const float* pts, const uint8_t* rgb, uint64_t P, const orc_intri
 /* focal length in pixels of the PCL/VTK-equivalent pin-hole used by the splat definition */
 float orc_splat_focal(const orc_intrinsics*);
 
+/* ---- ensemble-uncertainty view scoring: NBV_Net_Labeler::nbv_loop cases 2 and 3 (main.cpp:2039-2161) ----
+ * images: [V][E][H][W][4] uint8 in the channel order cv::imread(IMREAD_UNCHANGED) yields (channels 0..2 colour, 3 alpha).
+ * method 2: sum over pixels/channels of log(variance) where variance > 1e-10; method 3: mean colour variance + (1-mean alpha)^2.
+ * chosen (may be NULL): views to skip.  Returns argmax with the reference's strict '>' from -1e100 (-1 if none). */
+int orc_score_ensemble(const uint8_t* images, uint32_t V, uint32_t E, int W, int H, int method, const uint8_t* chosen,
+                       double* scores_out);
+
 #ifdef __cplusplus
 }
 #endif

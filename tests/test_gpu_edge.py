@@ -173,3 +173,28 @@ def test_error_behaviour(prv, synth, ctx):
     seq, gain, _ = c.get_greedy(4)
     assert seq[0] == 1
     c.close()
+
+
+@pytest.mark.parametrize("method,E", [(2, 2), (3, 5), (2, 5), (3, 2)])
+def test_ensemble_uncertainty_scoring(prv, orc, ctx, method, E):
+    """nbv_loop cases 2/3 (main.cpp:2039-2161) at the reference's render size (W/16 x H/16 = 80 x 45)."""
+    rng = np.random.default_rng(100 + method * 10 + E)
+    V, H, W = 37, 45, 80
+    base = rng.integers(0, 256, size=(V, 1, H, W, 4), dtype=np.int64)
+    noise = rng.integers(-6, 7, size=(V, E, H, W, 4))
+    images = np.clip(base + noise, 0, 255).astype(np.uint8)
+    images[:, :, :5] = images[:, :1, :5]          # identical rows across the ensemble: zero variance (skipped by method 2)
+    images[3] = images[3, :1]                    # a view with no uncertainty at all
+    chosen = np.zeros(V, dtype=np.uint8)
+    chosen[[0, 11]] = 1
+    o_best, o_scores = orc.score_ensemble(images, method, chosen)
+    g_best, g_scores = ctx.score_ensemble(images, method, chosen)
+    assert g_best == o_best and o_best >= 0
+    if method == 3 or E == 2:
+        assert np.array_equal(g_scores, o_scores)     # same sequence of double operations (log terms from the host table)
+    else:
+        np.testing.assert_allclose(g_scores, o_scores, rtol=1e-12, atol=0)
+    assert g_scores[0] == 0 and g_scores[11] == 0
+    # everything chosen -> no candidate
+    b, _ = ctx.score_ensemble(images, method, np.ones(V, dtype=np.uint8))
+    assert b == -1 and orc.score_ensemble(images, method, np.ones(V, dtype=np.uint8))[0] == -1
