@@ -378,7 +378,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--variant", type=int, default=2)
-    ap.add_argument("--cpu-views", type=int, default=4, help="views in the cpu_baseline sample")
+    ap.add_argument("--cpu-views", type=int, default=16, help="views in the cpu_baseline sample (~10-30 s of CPU work across the host cores)")
     ap.add_argument("--ref-views", type=int, default=2, help="views per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
