@@ -93,25 +93,6 @@ __device__ __forceinline__ void block_append(bool keep, uint32_t value, uint32_t
     __syncthreads();  // s_woff / s_base are reused by the next chunk
 }
 
-__device__ __forceinline__ void block_append2(bool keep, uint2 value, uint2* queue_view, uint32_t* count_view, uint32_t* s_woff, uint32_t* s_base) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
-    if (lane == 0) s_woff[warp] = __popc(bal);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int w = 0; w < 8; w++) {
-            const uint32_t c = s_woff[w];
-            s_woff[w] = tot;
-            tot += c;
-        }
-        *s_base = tot ? atomicAdd(count_view, tot) : 0u;
-    }
-    __syncthreads();
-    if (keep) queue_view[*s_base + s_woff[warp] + __popc(bal & ((1u << lane) - 1u))] = value;
-    __syncthreads();
-}
-
 // One block per 32x32 pixel region of one view (blockIdx.x = region, blockIdx.y = view); every thread owns 4 pixels,
 // one in each 32x8 row-tile (a warp covers an 8x4 patch per row-tile).
 // Region test: the region's rays lie inside the cone around the mean corner direction whose half-angle is the largest
@@ -278,16 +259,6 @@ __device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint3
     __syncthreads();
 }
 
-// chunk id -> view index (largest v with s_prefix[v] <= g)
-__device__ __forceinline__ uint32_t find_view(const uint32_t* s_prefix, uint32_t nviews, uint32_t g) {
-    uint32_t lo = 0, hi = nviews;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (s_prefix[mid] <= g) lo = mid; else hi = mid;
-    }
-    return lo;
-}
-
 __global__ void __launch_bounds__(256) coarse_kernel(const CastParams p) {
     __shared__ ViewConst s_vc;
     __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
@@ -335,6 +306,9 @@ __global__ void __launch_bounds__(256) coarse_kernel(const CastParams p) {
     }
 }
 
+// 64-thread blocks (= 64-ray chunks) measured best: 256 -> 128 -> 64 gains 2-4 % (less time behind the slowest warp of a
+// chunk); 48 registers / 20 blocks per SM beats 40 registers / 24 blocks and 32 / 32 (spills) by 3-8 %.
+constexpr int kMarchBlock = 64, kMarchMinBlocks = 20;
 template <int BS, int MINB>
 __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
     __shared__ ViewConst s_vc;
@@ -999,7 +973,6 @@ struct prv_ctx {
     std::string err;
     int variant = PRV_VARIANT_AXIS;
     int occ_coarse = 0, occ_march = 0, occ_greedy = 0;
-    int march_bs = 64;  // measured: 64 > 128 > 256 by 2-4 % (less time behind the slowest warp of a chunk)
     uint32_t occ_greedy_words = 0;
     bool greedy_persistent = false;
     // The cluster/DSMEM greedy is correct but measured slower than the grid-barrier kernel on B200 (C2 0.25 vs 0.21 ms,
@@ -1354,13 +1327,7 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
             p.tickets = ptr<uint32_t>(ctx->d_tickets) + 2 * li;
             if (ctx->occ_coarse == 0) {  // persistent grids = exactly one resident wave
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_coarse, coarse_kernel, 256, 0);
-                if (const char* e = getenv("PRV_MARCH_BS")) ctx->march_bs = atoi(e);
-                if (ctx->march_bs == 128)
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march, march_kernel<128, 10>, 128, 0);
-                else if (ctx->march_bs == 64)
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march, march_kernel<64, 20>, 64, 0);
-                else
-                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march, march_kernel<256, 5>, 256, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march, march_kernel<kMarchBlock, kMarchMinBlocks>, kMarchBlock, 0);
                 ctx->occ_coarse = std::max(1, ctx->occ_coarse);
                 ctx->occ_march = std::max(1, ctx->occ_march);
             }
@@ -1374,12 +1341,7 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
                 coarse_kernel<<<(uint32_t)(ctx->sm_count * ctx->occ_coarse), 256, 0, ctx->stream>>>(p);
             }
             Span s(ctx, K_MARCH, 1);
-            if (ctx->march_bs == 128)
-                march_kernel<128, 10><<<(uint32_t)(ctx->sm_count * ctx->occ_march), 128, 0, ctx->stream>>>(p);
-            else if (ctx->march_bs == 64)
-                march_kernel<64, 20><<<(uint32_t)(ctx->sm_count * ctx->occ_march), 64, 0, ctx->stream>>>(p);
-            else
-                march_kernel<256, 5><<<(uint32_t)(ctx->sm_count * ctx->occ_march), 256, 0, ctx->stream>>>(p);
+            march_kernel<kMarchBlock, kMarchMinBlocks><<<(uint32_t)(ctx->sm_count * ctx->occ_march), kMarchBlock, 0, ctx->stream>>>(p);
         } else {
             Span s(ctx, K_CAST, 1);
             if (ctx->variant == PRV_VARIANT_PLAIN)
