@@ -302,6 +302,12 @@ def run_own(args):
     e2e_value = (rays_per_step_local * world if not strong else V * w["W"] * w["H"]) * e2e_steps / e2e_dt
     assert e_seq.tolist() == seq.tolist(), "e2e and resident paths disagree"
 
+    per_rank = None
+    if dist is not None:
+        mine = {"rank": rank, "step_ms": float(sum(step_ms)) / args.steps, "cast_ms": timing["cast_ms"] / args.steps,
+                "greedy_ms": timing["greedy_ms"] / args.steps, "allgather_ms": timing["other_ms"] / args.steps, "marched": stats["marched"]}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -356,7 +362,7 @@ def run_own(args):
             "views_scored_per_sec": views_scored * world / max(1e-9, timing["greedy_ms"] / args.steps * 1e-3) if not strong else
                                     views_scored / max(1e-9, timing["greedy_ms"] / args.steps * 1e-3),
             "kernel_ms_per_step": {k: timing[k] / args.steps for k in ("cast_ms", "cull_ms", "march_ms", "count_ms", "greedy_ms", "other_ms")},
-            "cast_stats": stats, "greedy_len": int(len(seq)), "greedy_seq": [int(x) for x in seq], "coverage_rate": float(gains.sum()) / max(1, ctx.full_voxels)}
+            "per_rank": per_rank, "cast_stats": stats, "greedy_len": int(len(seq)), "greedy_seq": [int(x) for x in seq], "coverage_rate": float(gains.sum()) / max(1, ctx.full_voxels)}
     emit(line)
     if dist is not None:
         dist.destroy_process_group()

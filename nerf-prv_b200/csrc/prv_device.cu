@@ -1002,7 +1002,10 @@ struct prv_ctx {
     DevBuf d_views, d_view_ids, d_row_of_id;
     std::vector<ViewConst> h_views;
     std::vector<uint32_t> h_view_ids;
-    std::vector<uint32_t> h_row_of_id;  // view id -> row of the table the greedy runs over (kNone = absent)
+    std::vector<uint32_t> h_row_of_id;      // view id -> local row (kNone = absent)
+    std::vector<uint32_t> h_row_of_id_all;  // view id -> row of the all-gathered table
+    DevBuf d_row_of_id_all;
+    bool gather_ids_valid = false;
     uint32_t id_space = 0;
 
     // cast outputs
@@ -1245,6 +1248,7 @@ int upload_views(prv_ctx* ctx, const double* pose_world, const double* init_pos,
     ctx->cast_done = false;
     ctx->greedy_done = false;
     ctx->gathered = false;
+    ctx->gather_ids_valid = false;
     return PRV_OK;
 }
 
@@ -1367,7 +1371,8 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
 
 int greedy_impl(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter) {
     if (!ctx->cast_done) return fail(ctx, PRV_ERR_INVALID, "prv_greedy: no coverage bitsets resident (call prv_cast_* first)");
-    if (first_view >= ctx->id_space) return fail(ctx, PRV_ERR_INVALID, "prv_greedy: first_view %u out of range", first_view);
+    const std::vector<uint32_t>& h_map = ctx->gathered ? ctx->h_row_of_id_all : ctx->h_row_of_id;
+    if (first_view >= h_map.size()) return fail(ctx, PRV_ERR_INVALID, "prv_greedy: first_view %u out of range", first_view);
     const uint32_t words = ctx->map.words64;
     int rc;
     if ((rc = ensure(ctx, ctx->d_best, 8 * ((size_t)max_iter + 2)))) return rc;
@@ -1377,9 +1382,9 @@ int greedy_impl(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter) {
     CU(cudaMemsetAsync(ctx->d_cov[0].p, 0, 8 * (size_t)words, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_cov[1].p, 0, 8 * (size_t)words, ctx->stream));
     const uint32_t* ids = ctx->gathered ? ptr<uint32_t>(ctx->d_all_ids) : ptr<uint32_t>(ctx->d_view_ids);
-    const uint32_t* row_of_id = ptr<uint32_t>(ctx->d_row_of_id);
+    const uint32_t* row_of_id = ctx->gathered ? ptr<uint32_t>(ctx->d_row_of_id_all) : ptr<uint32_t>(ctx->d_row_of_id);
     // row index of first_view in the active table
-    const uint32_t first_row = ctx->h_row_of_id[first_view];
+    const uint32_t first_row = h_map[first_view];
     if (first_row == kNone) return fail(ctx, PRV_ERR_INVALID, "prv_greedy: first_view %u is not a resident view id", first_view);
     const size_t cov_bytes = (size_t)words * 8;
     // 1st choice: one thread-block cluster holding the whole table in distributed shared memory
@@ -1555,7 +1560,7 @@ void prv_destroy(prv_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     prv_comm_destroy(ctx);
     DevBuf* bufs[] = {&ctx->d_coarse, &ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
-                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_tickets, &ctx->d_arrive, &ctx->d_ens_images, &ctx->d_ens_terms, &ctx->d_ens_scores, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
+                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_tickets, &ctx->d_arrive, &ctx->d_ens_images, &ctx->d_ens_terms, &ctx->d_ens_scores, &ctx->d_row_of_id_all, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
                       &ctx->d_voxel_pix, &ctx->d_voxel_hit, &ctx->d_points, &ctx->d_best, &ctx->d_cov[0], &ctx->d_cov[1], &ctx->d_all_rows,
                       &ctx->d_all_ids, &ctx->d_cloud_xyz, &ctx->d_cloud_rgb, &ctx->d_corner, &ctx->d_rgba, &ctx->d_depth_img, &ctx->d_flush};
     for (DevBuf* b : bufs) release(*b);
@@ -2197,24 +2202,28 @@ int prv_allgather_bitsets_async(prv_ctx* ctx) {
     if ((rc = ensure(ctx, ctx->d_all_rows, (size_t)G * V * words * 8))) return rc;
     if ((rc = ensure(ctx, ctx->d_all_ids, (size_t)G * V * 4))) return rc;
     {
-        Span s(ctx, K_OTHER, 2);
-        int r = ctx->nccl.AllGather(ctx->d_bitsets.p, ctx->d_all_rows.p, (size_t)V * words, /*ncclUint64*/ 5, ctx->comm, ctx->stream);
-        if (r == 0) r = ctx->nccl.AllGather(ctx->d_view_ids.p, ctx->d_all_ids.p, (size_t)V, /*ncclUint32*/ 3, ctx->comm, ctx->stream);
+        Span s(ctx, K_OTHER, 1);
+        const int r = ctx->nccl.AllGather(ctx->d_bitsets.p, ctx->d_all_rows.p, (size_t)V * words, /*ncclUint64*/ 5, ctx->comm, ctx->stream);
         if (r != 0) return fail(ctx, PRV_ERR_NCCL, "ncclAllGather failed: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(r) : "?");
     }
-    // row_of_id for the gathered table (ids are a permutation of 0..G*V-1 by contract)
-    std::vector<uint32_t> ids((size_t)G * V);
-    CU(d2h(ctx, ids.data(), ctx->d_all_ids.p, ids.size() * 4));
-    CU(cudaStreamSynchronize(ctx->stream));
-    uint32_t max_id = 0;
-    for (uint32_t id : ids) max_id = std::max(max_id, id);
-    std::vector<uint32_t>& row_of_id = ctx->h_row_of_id;
-    row_of_id.assign((size_t)max_id + 1, kNone);
-    for (size_t r = 0; r < ids.size(); r++) row_of_id[ids[r]] = (uint32_t)r;
-    if ((rc = ensure(ctx, ctx->d_row_of_id, 4 * row_of_id.size()))) return rc;
-    CU(h2d(ctx, ctx->d_row_of_id.p, row_of_id.data(), 4 * row_of_id.size()));
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->id_space = max_id + 1;
+    if (!ctx->gather_ids_valid) {
+        // once per view set: gather the global view ids and build view id -> row of the gathered table (the per-step
+        // all-gather of the rows above stays fully asynchronous)
+        const int r = ctx->nccl.AllGather(ctx->d_view_ids.p, ctx->d_all_ids.p, (size_t)V, /*ncclUint32*/ 3, ctx->comm, ctx->stream);
+        if (r != 0) return fail(ctx, PRV_ERR_NCCL, "ncclAllGather failed: %s", ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(r) : "?");
+        std::vector<uint32_t> ids((size_t)G * V);
+        CU(d2h(ctx, ids.data(), ctx->d_all_ids.p, ids.size() * 4));
+        CU(cudaStreamSynchronize(ctx->stream));
+        uint32_t max_id = 0;
+        for (uint32_t id : ids) max_id = std::max(max_id, id);
+        std::vector<uint32_t>& row_of_id = ctx->h_row_of_id_all;
+        row_of_id.assign((size_t)max_id + 1, kNone);
+        for (size_t r2 = 0; r2 < ids.size(); r2++) row_of_id[ids[r2]] = (uint32_t)r2;
+        if ((rc = ensure(ctx, ctx->d_row_of_id_all, 4 * row_of_id.size()))) return rc;
+        CU(h2d(ctx, ctx->d_row_of_id_all.p, row_of_id.data(), 4 * row_of_id.size()));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->gather_ids_valid = true;
+    }
     ctx->gathered = true;
     ctx->g_rows = ptr<uint64_t>(ctx->d_all_rows);
     ctx->g_nrows = G * V;
