@@ -4,9 +4,9 @@ mkdir -p gpurun_out
 for N in 1 2 4 8; do
   for WL in C2 C3; do
     if [ $N -eq 1 ]; then
-      python bench.py --gpus 1 --workload $WL --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/scale_${WL}_n${N}.json 2> gpurun_out/scale_${WL}_n${N}.err
+      python bench.py --gpus 1 --workload $WL --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/scale_${WL}_n${N}.json 2> gpurun_out/scale_${WL}_n${N}.err
     else
-      python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600+N)) bench.py --gpus $N --workload $WL --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/scale_${WL}_n${N}.json 2> gpurun_out/scale_${WL}_n${N}.err
+      python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29600+N)) bench.py --gpus $N --workload $WL --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/scale_${WL}_n${N}.json 2> gpurun_out/scale_${WL}_n${N}.err
     fi
     python - <<PY
 import json
