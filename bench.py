@@ -353,12 +353,30 @@ def run_own(args):
         cpu = {"value": r / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%d of %d views of %s (dense cast + rows + greedy over the sampled rows), %.1f s" % (len(sample_ids), V, args.workload, dt)}
 
+    # the reference's own execution structure (one std::thread per voxel in batches of
+    # num_of_thread = 20, pose inverse per voxel, sparse lookup; main.cpp:124-130, 238-284) on one view of C1
+    ref_structure = None
+    if not args.no_cpu_baseline:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import oracle as orc
+            w1 = synth.build_workload(prv, "C1", n_views=1)
+            m1 = orc.Map.from_keys(w1["keys"], w1["map_rgb"], w1["resolution"])
+            t0 = time.perf_counter()
+            m1.precept_threads(_oracle_intr(orc, w1["intr"]), w1["pose_world"][0], w1["init_pos"][0], 1.0, 20)
+            dt = time.perf_counter() - t0
+            ref_structure = {"value": m1.n / dt, "unit": "voxel rays/s", "sample": "Perception_3D::precept of 1 view of C1 (%d voxels), %.2f s" % (m1.n, dt),
+                             "structure": "std::thread per voxel, batches of 20, joined per batch"}
+        except Exception as exc:  # never let the side baseline break the bench line
+            ref_structure = {"error": str(exc)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": _config(w, args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": c2["h2d_bytes"] // e2e_steps, "d2h_bytes_per_step": c2["d2h_bytes"] // e2e_steps,
                     "steps": e2e_steps, "host_memory": pinned_note},
             "gpu_launches": counters["kernel_launches"], "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "cpu_reference_structure": ref_structure,
             "views_scored_per_sec": views_scored * world / max(1e-9, timing["greedy_ms"] / args.steps * 1e-3) if not strong else
                                     views_scored / max(1e-9, timing["greedy_ms"] / args.steps * 1e-3),
             "kernel_ms_per_step": {k: timing[k] / args.steps for k in ("cast_ms", "cull_ms", "march_ms", "count_ms", "greedy_ms", "other_ms")},

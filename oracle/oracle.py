@@ -85,6 +85,8 @@ def lib():
     L.orc_cast_ray.restype = C.c_int
     L.orc_precept.argtypes = [C.c_void_p, P(Intrinsics), P(d), P(d), d, C.c_void_p, P(u32), P(CastStats)]
     L.orc_precept.restype = C.c_int
+    L.orc_precept_threads.argtypes = [C.c_void_p, P(Intrinsics), P(d), P(d), d, C.c_int, C.c_void_p, P(u32)]
+    L.orc_precept_threads.restype = C.c_int
     L.orc_cast_view_dense.argtypes = [C.c_void_p, P(Intrinsics), P(d), P(d), d, P(u32), P(f), P(CastStats), C.c_int]
     L.orc_cast_view_dense.restype = C.c_int
     L.orc_bitset_words.argtypes = [u32]
@@ -242,6 +244,16 @@ class Map:
         ip = np.ascontiguousarray(init_pos, dtype=np.float64)
         ok = lib().orc_precept(self._h, C.byref(intr), _ptr(pw, C.c_double), _ptr(ip, C.c_double), max_range,
                                out.ctypes.data_as(C.c_void_p), _ptr(ranks, C.c_uint32), None if stats is None else C.byref(stats))
+        return bool(ok), out, ranks
+
+    def precept_threads(self, intr, pose_world, init_pos, max_range=1.0, num_of_thread=20):
+        """precept with the reference's execution structure: one std::thread per voxel in batches of num_of_thread."""
+        out = np.zeros(self.n, dtype=POINT_DTYPE)
+        ranks = np.zeros(self.n, dtype=np.uint32)
+        pw = _d16(pose_world)
+        ip = np.ascontiguousarray(init_pos, dtype=np.float64)
+        ok = lib().orc_precept_threads(self._h, C.byref(intr), _ptr(pw, C.c_double), _ptr(ip, C.c_double), max_range, num_of_thread,
+                                       out.ctypes.data_as(C.c_void_p), _ptr(ranks, C.c_uint32))
         return bool(ok), out, ranks
 
     def cast_view_dense(self, intr, pose_world, init_pos, max_range=1.0, want_depth=True, stats=None, num_threads=0):

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <unordered_set>
 #include <vector>
 #ifdef _OPENMP
@@ -689,6 +690,55 @@ int orc_precept(const orc_map* map, const orc_intrinsics* in, const double view_
         out[i].b = map->rgb[3 * rank + 2];
         if (hit_rank_out) hit_rank_out[i] = rank;
     }
+    return 1;
+}
+
+namespace {
+void precept_one_voxel(const orc_map* map, const orc_intrinsics* in, const M4* pose, const float* origin, double max_range, uint32_t i,
+                       orc_point_xyzrgb* out, uint32_t* hit_rank_out) {
+    const float e[3] = {(float)key_to_coord(map->keys[3 * i + 0], map->resolution), (float)key_to_coord(map->keys[3 * i + 1], map->resolution),
+                        (float)key_to_coord(map->keys[3 * i + 2], map->resolution)};
+    const double end_3d[4] = {e[0], e[1], e[2], 1};
+    const M4 inv = m4_inverse(*pose);  // recomputed per voxel, main.cpp:244
+    double vertex[4];
+    m4_vec(inv, end_3d, vertex);
+    const float point_3d[3] = {(float)vertex[0], (float)vertex[1], (float)vertex[2]};
+    float pixel[2];
+    project_point_to_pixel(pixel, in, point_3d);
+    if (pixel[0] < 0 || pixel[0] > in->width || pixel[1] < 0 || pixel[1] > in->height) return;
+    if (pixel[0] != pixel[0] || pixel[1] != pixel[1]) return;
+    float end_point[3];
+    const uint32_t rank = cast_pixel(map, in, *pose, origin, (int)pixel[0], (int)pixel[1], max_range, end_point, nullptr);
+    if (rank == 0xFFFFFFFFu) return;
+    out[i].x = end_point[0];
+    out[i].y = end_point[1];
+    out[i].z = end_point[2];
+    out[i].r = map->rgb[3 * rank + 0];
+    out[i].g = map->rgb[3 * rank + 1];
+    out[i].b = map->rgb[3 * rank + 2];
+    if (hit_rank_out) hit_rank_out[i] = rank;
+}
+}  // namespace
+
+int orc_precept_threads(orc_map* map, const orc_intrinsics* in, const double view_pose_world[16], const double init_pos[3], double max_range,
+                        int num_of_thread, orc_point_xyzrgb* out, uint32_t* hit_rank_out) {
+    const uint32_t N = map->n();
+    std::memset(out, 0, (size_t)N * sizeof(orc_point_xyzrgb));
+    if (hit_rank_out)
+        for (uint32_t i = 0; i < N; i++) hit_rank_out[i] = 0xFFFFFFFFu;
+    float origin[3];
+    if (!view_origin(map, init_pos, origin)) return 0;
+    const M4 pose = m4_load(view_pose_world);
+    const bool was_slow = map->slow;
+    map->slow = true;  // sparse (tree-like) lookup
+    std::vector<std::thread> precept_process;
+    precept_process.reserve(N);
+    for (uint32_t i = 0; i < N; i += (uint32_t)num_of_thread) {  // main.cpp:125-130
+        for (uint32_t j = 0; j < (uint32_t)num_of_thread && i + j < N; j++)
+            precept_process.emplace_back(precept_one_voxel, map, in, &pose, origin, max_range, i + j, out, hit_rank_out);
+        for (uint32_t j = 0; j < (uint32_t)num_of_thread && i + j < N; j++) precept_process[i + j].join();
+    }
+    map->slow = was_slow;
     return 1;
 }
 

@@ -102,6 +102,12 @@ int orc_cast_ray(const orc_map*, const float origin[3], const float direction[3]
 int orc_precept(const orc_map*, const orc_intrinsics*, const double view_pose_world[16], const double init_pos[3],
                 double max_range, orc_point_xyzrgb* out, uint32_t* hit_rank_out, orc_cast_stats* stats);
 
+/* Same as orc_precept but with the reference's own execution structure (main.cpp:124-130): one std::thread per voxel,
+ * created and joined in batches of num_of_thread, each recomputing the pose inverse, with the hash-set (sparse) lookup.
+ * Only for the "reference-faithful structure" CPU baseline of BASELINE.md section 3; results equal orc_precept. */
+int orc_precept_threads(orc_map*, const orc_intrinsics*, const double view_pose_world[16], const double init_pos[3],
+                        double max_range, int num_of_thread, orc_point_xyzrgb* out, uint32_t* hit_rank_out);
+
 /* ---- dense per-pixel mode (north-star "one ray per pixel"): same per-ray code as precept from
  * project_pixel_to_ray_end on, for every integer pixel (x,y) in [0,W)x[0,H).
  * hit_rank_out: H*W (row-major, 0xFFFFFFFF = none); depth_out (optional): sqrt of castRay's d^2, float. */

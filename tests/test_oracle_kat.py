@@ -220,3 +220,13 @@ def test_splat_definition(orc):
     assert rgba[0, 0].tolist() == [255, 255, 255, 0] and depth[0, 0] == 0.0
     # equal depth overlap: the lower point index wins (points 0 and 4 both at z = 1)
     assert index[15, 22] == 0
+
+
+def test_reference_thread_structure_equals_plain_precept(prv, orc, synth):
+    """main.cpp:124-130: one std::thread per voxel in batches of num_of_thread; same cloud as the plain loop."""
+    w = synth.build_workload(prv, "C1", n_views=2, size=(160, 120), n_points=6000)
+    m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
+    it = orc.make_intrinsics(w["intr"].width, w["intr"].height, w["intr"].fx, w["intr"].fy, w["intr"].ppx, w["intr"].ppy, 2, list(w["intr"].coeffs))
+    ok, a, ra = m.precept(it, w["pose_world"][1], w["init_pos"][1])
+    ok2, b, rb = m.precept_threads(it, w["pose_world"][1], w["init_pos"][1], num_of_thread=20)
+    assert ok and ok2 and np.array_equal(ra, rb) and np.array_equal(a, b) and (ra != orc.NONE).sum() > 50
