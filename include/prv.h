@@ -130,6 +130,11 @@ int prv_host_build_map(const float* pts_xyz, const uint8_t* rgb, uint64_t P, dou
 /* ground_truth_model (Share_Data.hpp:258,458): occupied leaf keys in leaf order + voxel colours (may be NULL). */
 int prv_set_map(prv_ctx* ctx, const uint16_t* keys /* N x 3 */, const uint8_t* rgb /* N x 3 */, uint32_t N,
                 double resolution);
+/* GPU ingest: the same insertion rule as prv_host_build_map (main.cpp:1005-1036: key per point, a voxel keeps the colour
+ * of its FIRST point; leaf order) executed on the device from the normalised cloud_ground_truth points, then prv_set_map.
+ * rgb may be NULL.  prv_get_map returns the resulting leaf keys / colours (prv_full_voxels() entries). */
+int prv_set_map_from_cloud(prv_ctx* ctx, const float* xyz /* P x 3 */, const uint8_t* rgb /* P x 3 */, uint64_t P, double resolution);
+int prv_get_map(prv_ctx* ctx, uint16_t* keys_out /* N x 3 or NULL */, uint8_t* rgb_out /* N x 3 or NULL */);
 /* share_data->color_intrinsics (Share_Data.hpp:388-399) and castRay's maxRange (main.cpp:258: 1.0) */
 int prv_set_camera(prv_ctx* ctx, const prv_intrinsics* intr, double max_range);
 /* candidate views: view_pose_world (main.cpp:109) and View::init_pos (snapped to a voxel centre on upload, main.cpp:112-114) */

@@ -95,6 +95,8 @@ def lib():
         "prv_host_normalize_cloud": (i, [P(f), u64, d, P(d)]),
         "prv_host_build_map": (i, [P(f), P(u8), u64, d, P(u16), P(u8), P(u32)]),
         "prv_set_map": (i, [vp, P(u16), P(u8), u32, d]),
+        "prv_set_map_from_cloud": (i, [vp, P(f), P(u8), u64, d]),
+        "prv_get_map": (i, [vp, P(u16), P(u8)]),
         "prv_set_camera": (i, [vp, P(Intrinsics), d]),
         "prv_set_views": (i, [vp, P(d), P(d), u32]),
         "prv_set_view_ids": (i, [vp, P(u32), u32]),
@@ -286,6 +288,19 @@ class Context:
         k = np.ascontiguousarray(keys, dtype=np.uint16)
         col = None if rgb is None else np.ascontiguousarray(rgb, dtype=np.uint8)
         self._chk(lib().prv_set_map(self._h, _p(k, C.c_uint16), _p(col, C.c_uint8), k.shape[0], resolution))
+
+    def set_map_from_cloud(self, xyz, rgb, resolution):
+        """GPU ingest of the normalised cloud (same rule as host_build_map)."""
+        p = np.ascontiguousarray(xyz, dtype=np.float32)
+        c = None if rgb is None else np.ascontiguousarray(rgb, dtype=np.uint8)
+        self._chk(lib().prv_set_map_from_cloud(self._h, _p(p, C.c_float), _p(c, C.c_uint8), p.shape[0], resolution))
+
+    def get_map(self):
+        n = self.full_voxels
+        keys = np.zeros((n, 3), dtype=np.uint16)
+        rgb = np.zeros((n, 3), dtype=np.uint8)
+        self._chk(lib().prv_get_map(self._h, _p(keys, C.c_uint16), _p(rgb, C.c_uint8)))
+        return keys, rgb
 
     def set_camera(self, intr, max_range=1.0):
         self.intr = intr

@@ -1,6 +1,8 @@
 // prv_device.cu -- device side of include/prv.h: context, HBM layout, kernel launches, NCCL glue.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -Xcompiler -ffp-contract=off (see build.py).
 #include <cooperative_groups.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdint.h>
@@ -571,6 +573,50 @@ __global__ void __launch_bounds__(256) map_rank_kernel(MapBuild b) {
     b.leaf_of_raster[b.prefix[w] + __popc(b.bitmap[w] & ((1u << (q0 & 31)) - 1u))] = i;
 }
 
+// GPU ingest: cloud points -> leaf-ordered unique keys + first-point colours ------------------------
+// key = (int)floor(resolution_factor * (double)coord) + 32768 (coordToKeyChecked, main.cpp:1015), invalid points sort last
+__global__ void __launch_bounds__(256) ingest_keys_kernel(const float* __restrict__ xyz, uint32_t P, double resolution_factor,
+                                                          unsigned long long* __restrict__ codes, uint32_t* __restrict__ index) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    uint16_t k[3];
+    bool ok = true;
+    for (int a = 0; a < 3; a++) {
+        const int scaled = (int)floor(prvk::dmul(resolution_factor, (double)xyz[3 * (size_t)i + a])) + prv::kTreeMaxVal;
+        ok = ok && scaled >= 0 && scaled < 2 * prv::kTreeMaxVal;
+        k[a] = (uint16_t)scaled;
+    }
+    codes[i] = ok ? prv::morton_code(k[0], k[1], k[2]) : (1ull << 48);
+    index[i] = i;
+}
+
+// head[i] = 1 when sorted entry i starts a new voxel (head[P] = 0 pads the scan so pos[P] = number of voxels)
+__global__ void __launch_bounds__(256) ingest_heads_kernel(const unsigned long long* __restrict__ codes, uint32_t P, uint32_t* __restrict__ head) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > P) return;
+    uint32_t h = 0;
+    if (i < P) {
+        const unsigned long long c = codes[i];
+        h = (c < (1ull << 48)) && (i == 0 || codes[i - 1] != c) ? 1u : 0u;
+    }
+    head[i] = h;
+}
+
+__global__ void __launch_bounds__(256) ingest_compact_kernel(const unsigned long long* __restrict__ codes, const uint32_t* __restrict__ index,
+                                                             const uint32_t* __restrict__ head, const uint32_t* __restrict__ pos, uint32_t P,
+                                                             const uint8_t* __restrict__ rgb_in, uint16_t* __restrict__ keys_out, uint8_t* __restrict__ rgb_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P || !head[i]) return;
+    const uint32_t j = pos[i];
+    uint16_t k[3];
+    prv::morton_decode(codes[i], k);
+    const uint32_t src = index[i];
+    for (int a = 0; a < 3; a++) {
+        keys_out[3 * (size_t)j + a] = k[a];
+        rgb_out[3 * (size_t)j + a] = rgb_in[3 * (size_t)src + a];
+    }
+}
+
 // coverage_count[v] = popcount(vis[v])
 __global__ void __launch_bounds__(256) popcount_rows_kernel(const uint64_t* rows, uint32_t words64, uint32_t* counts) {
     __shared__ uint32_t s_red[8];
@@ -976,6 +1022,8 @@ struct prv_ctx {
     int greedy_blocks_per_sm = 2;
     DevBuf d_arrive;
     DevBuf d_ens_images, d_ens_terms, d_ens_scores;
+    DevBuf d_ing_xyz, d_ing_rgb, d_ing_k0, d_ing_k1, d_ing_v0, d_ing_v1, d_ing_pos, d_ing_tmp;
+    std::vector<uint8_t> h_rgb;
 
     // map
     bool have_map = false;
@@ -1553,7 +1601,8 @@ void prv_destroy(prv_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     prv_comm_destroy(ctx);
     DevBuf* bufs[] = {&ctx->d_coarse, &ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
-                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_tickets, &ctx->d_arrive, &ctx->d_ens_images, &ctx->d_ens_terms, &ctx->d_ens_scores, &ctx->d_row_of_id_all, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
+                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_tickets, &ctx->d_arrive, &ctx->d_ens_images, &ctx->d_ens_terms, &ctx->d_ens_scores, &ctx->d_row_of_id_all, &ctx->d_ing_xyz, &ctx->d_ing_rgb, &ctx->d_ing_k0,
+                      &ctx->d_ing_k1, &ctx->d_ing_v0, &ctx->d_ing_v1, &ctx->d_ing_pos, &ctx->d_ing_tmp, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
                       &ctx->d_voxel_pix, &ctx->d_voxel_hit, &ctx->d_points, &ctx->d_best, &ctx->d_cov[0], &ctx->d_cov[1], &ctx->d_all_rows,
                       &ctx->d_all_ids, &ctx->d_cloud_xyz, &ctx->d_cloud_rgb, &ctx->d_corner, &ctx->d_rgba, &ctx->d_depth_img, &ctx->d_flush};
     for (DevBuf* b : bufs) release(*b);
@@ -1590,7 +1639,8 @@ int prv_set_variant(prv_ctx* ctx, int variant) {
     return PRV_OK;
 }
 
-int prv_set_map(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, uint32_t N, double resolution) {
+// keys/rgb: host copies in leaf order.  device_ready: d_keys / d_rgb already hold the same data (GPU ingest path).
+static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, uint32_t N, double resolution, bool device_ready) {
     if (!ctx) return PRV_ERR_INVALID;
     if (!keys || N == 0 || !(resolution > 0)) return fail(ctx, PRV_ERR_INVALID, "prv_set_map: null/empty map or bad resolution");
     CU(cudaSetDevice(ctx->device));
@@ -1628,14 +1678,16 @@ int prv_set_map(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, uint32_t
     if ((rc = ensure(ctx, ctx->d_bitmap, nwords * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_prefix, nwords * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_leaf_of_raster, (size_t)N * 4))) return rc;
-    if ((rc = ensure(ctx, ctx->d_keys, (size_t)N * 6))) return rc;
-    if ((rc = ensure(ctx, ctx->d_rgb, (size_t)N * 3))) return rc;
-    // the only host->device traffic: leaf keys and colours; every table is built by kernels
-    CU(h2d(ctx, ctx->d_keys.p, keys, (size_t)N * 6));
-    if (rgb)
-        CU(h2d(ctx, ctx->d_rgb.p, rgb, (size_t)N * 3));
-    else
-        CU(cudaMemsetAsync(ctx->d_rgb.p, 0, (size_t)N * 3, ctx->stream));
+    if (!device_ready) {
+        if ((rc = ensure(ctx, ctx->d_keys, (size_t)N * 6))) return rc;
+        if ((rc = ensure(ctx, ctx->d_rgb, (size_t)N * 3))) return rc;
+        // the only host->device traffic: leaf keys and colours; every table is built by kernels
+        CU(h2d(ctx, ctx->d_keys.p, keys, (size_t)N * 6));
+        if (rgb)
+            CU(h2d(ctx, ctx->d_rgb.p, rgb, (size_t)N * 3));
+        else
+            CU(cudaMemsetAsync(ctx->d_rgb.p, 0, (size_t)N * 3, ctx->stream));
+    }
     CU(cudaMemsetAsync(ctx->d_coarse.p, 0, coarse_words * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_bitmap_pad.p, 0, pad_words * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_bitmap.p, 0, nwords * 4, ctx->stream));
@@ -1704,6 +1756,78 @@ int prv_set_map(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, uint32_t
     ctx->V = 0;
     ctx->cast_done = false;
     ctx->greedy_done = false;
+    return PRV_OK;
+}
+
+int prv_set_map(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, uint32_t N, double resolution) {
+    return set_map_impl(ctx, keys, rgb, N, resolution, false);
+}
+
+int prv_set_map_from_cloud(prv_ctx* ctx, const float* xyz, const uint8_t* rgb, uint64_t P, double resolution) {
+    if (!ctx) return PRV_ERR_INVALID;
+    if (!xyz || P == 0 || P > 0x7FFFFFFFull || !(resolution > 0)) return fail(ctx, PRV_ERR_INVALID, "prv_set_map_from_cloud: null/empty cloud or bad resolution");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    const uint32_t n = (uint32_t)P;
+    if ((rc = ensure(ctx, ctx->d_ing_xyz, P * 12))) return rc;
+    if ((rc = ensure(ctx, ctx->d_ing_rgb, P * 3))) return rc;
+    if ((rc = ensure(ctx, ctx->d_ing_k0, P * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->d_ing_k1, P * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->d_ing_v0, (P + 1) * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_ing_v1, P * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_ing_pos, (P + 1) * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_keys, P * 6))) return rc;
+    if ((rc = ensure(ctx, ctx->d_rgb, P * 3))) return rc;
+    CU(h2d(ctx, ctx->d_ing_xyz.p, xyz, P * 12));
+    if (rgb)
+        CU(h2d(ctx, ctx->d_ing_rgb.p, rgb, P * 3));
+    else
+        CU(cudaMemsetAsync(ctx->d_ing_rgb.p, 0, P * 3, ctx->stream));
+    size_t tmp_sort = 0, tmp_scan = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, ptr<unsigned long long>(ctx->d_ing_k0), ptr<unsigned long long>(ctx->d_ing_k1),
+                                    ptr<uint32_t>(ctx->d_ing_v0), ptr<uint32_t>(ctx->d_ing_v1), (int)n, 0, 49, ctx->stream);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, ptr<uint32_t>(ctx->d_ing_v0), ptr<uint32_t>(ctx->d_ing_pos), (int)n + 1, ctx->stream);
+    if ((rc = ensure(ctx, ctx->d_ing_tmp, std::max(tmp_sort, tmp_scan)))) return rc;
+    size_t tmp_bytes = ctx->d_ing_tmp.cap;
+    {
+        Span sp(ctx, K_OTHER, 5);
+        ingest_keys_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ptr<float>(ctx->d_ing_xyz), n, 1.0 / resolution, ptr<unsigned long long>(ctx->d_ing_k0),
+                                                                   ptr<uint32_t>(ctx->d_ing_v0));
+        // stable LSD radix sort on the 48-bit Morton code (+1 bit: invalid points sort last): points of one voxel stay in
+        // cloud order, so the first one is the point whose colour the reference keeps (main.cpp:1015-1021)
+        CU(cub::DeviceRadixSort::SortPairs(ctx->d_ing_tmp.p, tmp_bytes, ptr<unsigned long long>(ctx->d_ing_k0), ptr<unsigned long long>(ctx->d_ing_k1),
+                                           ptr<uint32_t>(ctx->d_ing_v0), ptr<uint32_t>(ctx->d_ing_v1), (int)n, 0, 49, ctx->stream));
+        ingest_heads_kernel<<<(n + 1 + 255) / 256, 256, 0, ctx->stream>>>(ptr<unsigned long long>(ctx->d_ing_k1), n, ptr<uint32_t>(ctx->d_ing_v0));
+        tmp_bytes = ctx->d_ing_tmp.cap;
+        CU(cub::DeviceScan::ExclusiveSum(ctx->d_ing_tmp.p, tmp_bytes, ptr<uint32_t>(ctx->d_ing_v0), ptr<uint32_t>(ctx->d_ing_pos), (int)n + 1, ctx->stream));
+        ingest_compact_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ptr<unsigned long long>(ctx->d_ing_k1), ptr<uint32_t>(ctx->d_ing_v1), ptr<uint32_t>(ctx->d_ing_v0),
+                                                                      ptr<uint32_t>(ctx->d_ing_pos), n, ptr<uint8_t>(ctx->d_ing_rgb), ptr<uint16_t>(ctx->d_keys),
+                                                                      ptr<uint8_t>(ctx->d_rgb));
+    }
+    CU(cudaGetLastError());
+    uint32_t N = 0;
+    CU(d2h(ctx, &N, ptr<uint32_t>(ctx->d_ing_pos) + n, 4));
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (N == 0) return fail(ctx, PRV_ERR_INVALID, "prv_set_map_from_cloud: no point has a valid key");
+    std::vector<uint16_t> keys((size_t)N * 3);
+    std::vector<uint8_t> col((size_t)N * 3);
+    CU(d2h(ctx, keys.data(), ctx->d_keys.p, (size_t)N * 6));
+    CU(d2h(ctx, col.data(), ctx->d_rgb.p, (size_t)N * 3));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->h_rgb = col;
+    return set_map_impl(ctx, keys.data(), col.data(), N, resolution, true);
+}
+
+int prv_get_map(prv_ctx* ctx, uint16_t* keys_out, uint8_t* rgb_out) {
+    if (!ctx) return PRV_ERR_INVALID;
+    if (!ctx->have_map) return fail(ctx, PRV_ERR_INVALID, "prv_get_map: no map set");
+    CU(cudaSetDevice(ctx->device));
+    const size_t N = ctx->map.n_occ;
+    if (keys_out) std::memcpy(keys_out, ctx->h_keys.data(), N * 6);
+    if (rgb_out) {
+        CU(d2h(ctx, rgb_out, ctx->d_rgb.p, N * 3));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     return PRV_OK;
 }
 

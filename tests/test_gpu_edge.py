@@ -198,3 +198,28 @@ def test_ensemble_uncertainty_scoring(prv, orc, ctx, method, E):
     # everything chosen -> no candidate
     b, _ = ctx.score_ensemble(images, method, np.ones(V, dtype=np.uint8))
     assert b == -1 and orc.score_ensemble(images, method, np.ones(V, dtype=np.uint8))[0] == -1
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_gpu_ingest_matches_host_map_build(prv, orc, synth, name):
+    """prv_set_map_from_cloud (GPU: key per point, stable Morton sort, first colour wins) == prv_host_build_map == oracle."""
+    w = synth.build_workload(prv, name, n_views=2, size=(64, 48))
+    cloud = w["cloud"].copy()
+    rgb = w["cloud_rgb"].copy()
+    # a few points outside the key range (coordToKeyChecked fails -> skipped) and duplicates with different colours
+    cloud = np.concatenate([cloud, [[70.0, 0, 0], [0, -70.0, 0]], cloud[:50]]).astype(np.float32)
+    rgb = np.concatenate([rgb, [[1, 2, 3], [4, 5, 6]], 255 - rgb[:50]]).astype(np.uint8)
+    c = prv.Context(0)
+    c.set_map_from_cloud(cloud, rgb, w["resolution"])
+    keys, col = c.get_map()
+    h_keys, h_col = prv.host_build_map(cloud, rgb, w["resolution"])
+    assert np.array_equal(keys, h_keys) and np.array_equal(col, h_col)
+    m = orc.Map.from_points(cloud, rgb, w["resolution"])
+    assert np.array_equal(keys, m.keys) and np.array_equal(col, m.rgb)
+    # and the map works: cast equals the cast on the host-built map
+    c.set_camera(w["intr"], 1.0)
+    b1, n1, _, _ = c.cast_views(w["pose_world"], w["init_pos"], mode=prv.MODE_DENSE)
+    c.set_map(h_keys, h_col, w["resolution"])
+    b2, n2, _, _ = c.cast_views(w["pose_world"], w["init_pos"], mode=prv.MODE_DENSE)
+    assert np.array_equal(b1, b2) and n1.sum() > 100
+    c.close()
