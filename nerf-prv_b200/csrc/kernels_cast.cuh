@@ -1,0 +1,444 @@
+// kernels_cast.cuh -- ray-cast kernels: cull / coarse / march pipeline (variant AXIS), single-kernel PLAIN/FAST variants, voxel-mode projection and gathers
+// Part of the single translation unit prv_device.cu (included there, in order); see DESIGN.md section 4.
+#pragma once
+
+// deterministic counters, one set per view: block-reduce, then one atomic per counter per block (per-warp atomics on
+// one address serialise in L2 and were measured to bound the whole kernel)
+__device__ __forceinline__ void commit_stats(unsigned long long* view_stats, uint32_t rays, uint32_t probes, uint32_t hits, uint32_t steps) {
+    __shared__ uint32_t s_cnt[4][8];
+    uint32_t c[4] = {rays, probes, hits, steps};
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        for (int o = 16; o > 0; o >>= 1) c[i] += __shfl_down_sync(0xFFFFFFFFu, c[i], o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0)
+        for (int i = 0; i < 4; i++) s_cnt[i][warp] = c[i];
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        unsigned long long t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_cnt[threadIdx.x][w];
+        if (t) atomicAdd(view_stats + threadIdx.x, t);
+    }
+}
+
+__device__ __forceinline__ void load_view_const(ViewConst& dst, const ViewConst* src) {
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(&dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(ViewConst) / 4); i += blockDim.x) d32[i] = s32[i];
+    __syncthreads();
+}
+
+__device__ __forceinline__ void write_hit(const CastParams& p, const ViewConst& vc, uint32_t view, unsigned long long pid, const CastResult& res) {
+    if (res.rank != kNone) {
+        uint32_t* row = p.bitsets32 + (size_t)view * (2u * p.map.words64);
+        const uint32_t bit = 1u << (res.rank & 31);
+        uint32_t* w = row + (res.rank >> 5);
+        if (!(*reinterpret_cast<volatile uint32_t*>(w) & bit)) atomicOr(w, bit);
+    }
+    if (p.pix_hit) {
+        p.pix_hit[(size_t)view * p.pix_stride + pid] = res.rank;
+        if (p.pix_depth) {
+            float d = 0.0f;
+            if (res.rank != kNone) d = (float)__dsqrt_rn(dist_sq_at(vc, p.map.resolution, res.k0, res.k1, res.k2));
+            p.pix_depth[(size_t)view * p.pix_stride + pid] = d;
+        }
+    }
+}
+
+// ---- AXIS pipeline ------------------------------------------------------------------------------------------------
+// kernel 1 (cull_kernel):   every pixel, loose float slab test against the grown AABB; survivors -> queue 1
+// kernel 2 (coarse_kernel): dense warps over queue 1, conservative coarse-brick walk; survivors -> queue 2
+// kernel 3 (march_kernel):  dense warps over queue 2, the exact castRay march
+// Kernels 2 and 3 run persistent blocks that pull 256-ray chunks of a flattened (view, chunk) list with an atomic
+// ticket, so expensive and cheap chunks balance across the 148 SMs and there is no partial last wave.
+
+// block-level stream compaction of `keep` lanes into a per-view queue: one atomic per block
+__device__ __forceinline__ void block_append(bool keep, uint32_t value, uint32_t* queue_view, uint32_t* count_view, uint32_t* s_woff, uint32_t* s_base) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) s_woff[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 8; w++) {
+            const uint32_t c = s_woff[w];
+            s_woff[w] = tot;
+            tot += c;
+        }
+        *s_base = tot ? atomicAdd(count_view, tot) : 0u;
+    }
+    __syncthreads();
+    if (keep) queue_view[*s_base + s_woff[warp] + __popc(bal & ((1u << lane) - 1u))] = value;
+    __syncthreads();  // s_woff / s_base are reused by the next chunk
+}
+
+// One block per 32x32 pixel region of one view (blockIdx.x = region, blockIdx.y = view); every thread owns 4 pixels,
+// one in each 32x8 row-tile (a warp covers an 8x4 patch per row-tile).
+// Region test: the region's rays lie inside the cone around the mean corner direction whose half-angle is the largest
+// corner angle (the pixel->direction map is projective up to the mild, host-checked lens distortion, for which the
+// corners are taken 2 pixels outside the region); if that cone misses the bounding sphere of the grown AABB, no ray
+// of the region can touch the AABB and the per-pixel tests are skipped.
+template <bool MASKED>
+__global__ void __launch_bounds__(256) cull_kernel(const CastParams p) {
+    __shared__ ViewConst s_vc;
+    __shared__ uint32_t s_woff[4][8];
+    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_rays[8];
+    __shared__ int s_skip;
+    const uint32_t view = blockIdx.y + p.view_base;
+    load_view_const(s_vc, p.views + view);
+    const ViewConst& vc = s_vc;
+    const int regions_x = (p.GW + 31) >> 5;
+    const int region_x = blockIdx.x % regions_x, region_y = blockIdx.x / regions_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool view_ok = (vc.flags & kViewInMap) && !(vc.flags & kViewInObject);
+    const bool fast = (vc.flags & kViewFastOk) != 0;
+
+    if (threadIdx.x < 32) {
+        // Region test (warp 0): the region's rays lie inside the pyramid spanned by the four corner rays taken 2 px
+        // outside the region (the pixel->direction map is affine up to the lens distortion, whose deviation inside any
+        // region was verified on the host to stay within that margin).  If all eight corners of the AABB grown by
+        // 2 voxels lie outside one side plane of the pyramid, no ray of the region can touch the AABB.
+        // lane = plane (0..3) * 8 + box corner (0..7): 32 dot products, one ballot.
+        bool skip = false;
+        if (!MASKED && view_ok && fast && p.cam.region_cull_ok) {
+            const int plane = lane >> 3, corner = lane & 7;
+            // pyramid corners counter-clockwise in pixel space: (x0,y0) (x1,y0) (x1,y1) (x0,y1)
+            const float x0 = (float)((region_x << 5) - 2), x1 = (float)((region_x << 5) + 33);
+            const float y0 = (float)((region_y << 5) - 2), y1 = (float)((region_y << 5) + 33);
+            const float ax = (plane == 0 || plane == 3) ? x0 : x1, ay = (plane == 0 || plane == 1) ? y0 : y1;   // corner `plane`
+            const float bx = (plane == 0 || plane == 1) ? x1 : x0, by = (plane == 1 || plane == 2) ? y1 : y0;   // corner `plane+1`
+            float adx, ady, adz, bdx, bdy, bdz, cdx, cdy, cdz;
+            ray_direction_approx(p.cam, vc, ax, ay, adx, ady, adz);
+            ray_direction_approx(p.cam, vc, bx, by, bdx, bdy, bdz);
+            ray_direction_approx(p.cam, vc, 0.5f * (x0 + x1), 0.5f * (y0 + y1), cdx, cdy, cdz);  // interior reference ray
+            // plane through the origin containing corner rays a and b; orient the normal away from the interior ray
+            float nx = ady * bdz - adz * bdy, ny = adz * bdx - adx * bdz, nz = adx * bdy - ady * bdx;
+            const float sgn = (nx * cdx + ny * cdy + nz * cdz) > 0.0f ? -1.0f : 1.0f;
+            nx *= sgn; ny *= sgn; nz *= sgn;
+            const float inv_n = rsqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
+            const float px = ((corner & 1) ? p.map.bmax[0] : p.map.bmin[0]) - vc.origin[0];
+            const float py = ((corner & 2) ? p.map.bmax[1] : p.map.bmin[1]) - vc.origin[1];
+            const float pz = ((corner & 4) ? p.map.bmax[2] : p.map.bmin[2]) - vc.origin[2];
+            const float dist = fmaf(nx, px, fmaf(ny, py, nz * pz)) * inv_n;  // signed distance of the box corner to the plane
+            const bool outside = dist > 1.0e-5f;                             // float error here is ~1e-7 m
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, outside);
+            skip = ((bal & 0xFFu) == 0xFFu) || ((bal & 0xFF00u) == 0xFF00u) || ((bal & 0xFF0000u) == 0xFF0000u) || ((bal & 0xFF000000u) == 0xFF000000u);
+        }
+        if (lane == 0) s_skip = skip ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_skip != 0) {
+        // the whole region provably misses: record "no hit" for its pixels and leave (no compaction protocol)
+        if (p.pix_hit) {
+            const int px = (region_x << 5) + ((warp & 3) << 3) + (lane & 7);
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
+                if (px < p.GW && py < p.GH) {
+                    const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
+                    p.pix_hit[o] = kNone;
+                    if (p.pix_depth) p.pix_depth[o] = 0.0f;
+                }
+            }
+        }
+        if (threadIdx.x == 0) {
+            const int w = min(32, p.GW - (region_x << 5)), h = min(32, p.GH - (region_y << 5));
+            atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)(w * h));
+        }
+        return;
+    }
+    const bool skip = false;
+
+    uint32_t keep_mask = 0;  // bit t: this thread's pixel in row-tile t survives
+    uint32_t pids[4];
+    uint32_t nrays = 0;
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        const int px = (region_x << 5) + ((warp & 3) << 3) + (lane & 7);
+        const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
+        const bool in_grid = px < p.GW && py < p.GH;
+        const unsigned long long pid = (unsigned long long)py * p.GW + px;
+        pids[t] = ((uint32_t)py << 16) | (uint32_t)px;  // queues carry (y,x) packed: no division downstream
+        bool active = in_grid && view_ok;
+        if (MASKED && active) {
+            const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
+            active = (w >> (pid & 31)) & 1u;
+        }
+        bool survive = false;
+        if (active && !skip) {
+            if (!fast) {
+                survive = true;  // this view needs the literal march (max-range test): no cull
+            } else {
+                float dx, dy, dz;
+                ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
+                survive = !loose_miss(p.map, vc, dx, dy, dz);
+            }
+        }
+        if (in_grid && !survive && p.pix_hit && (!MASKED || active)) {
+            p.pix_hit[(size_t)view * p.pix_stride + pid] = kNone;
+            if (p.pix_depth) p.pix_depth[(size_t)view * p.pix_stride + pid] = 0.0f;
+        }
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, survive);
+        nrays += __popc(__ballot_sync(0xFFFFFFFFu, active));
+        if (survive) keep_mask |= 1u << t;
+        if (lane == 0) s_woff[t][warp] = __popc(bal);
+        // lane-local rank within the warp for this row-tile, kept in the high bits
+        keep_mask |= (uint32_t)__popc(bal & ((1u << lane) - 1u)) << (8 + 6 * t);
+    }
+    if (lane == 0) s_rays[warp] = nrays;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0, rays = 0;
+        for (int t = 0; t < 4; t++)
+            for (int w = 0; w < 8; w++) {
+                const uint32_t c = s_woff[t][w];
+                s_woff[t][w] = tot;
+                tot += c;
+            }
+        for (int w = 0; w < 8; w++) rays += s_rays[w];
+        s_base = tot ? atomicAdd(p.qcount + view, tot) : 0u;
+        if (rays) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)rays);
+    }
+    __syncthreads();
+    if (keep_mask & 0xFu) {
+        uint32_t* q = p.queue + (size_t)view * p.queue_cap + s_base;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+            if (keep_mask & (1u << t)) q[s_woff[t][warp] + ((keep_mask >> (8 + 6 * t)) & 63u)] = pids[t];
+    }
+}
+
+// exclusive prefix of chunk counts (chunk = blockDim.x rays) over the views of this launch -> s_prefix[0..nviews]
+__device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint32_t nviews, uint32_t* s_prefix) {
+    const uint32_t chunk = blockDim.x;
+    __shared__ uint32_t s_part[8];
+    // each thread owns a contiguous run of views
+    const uint32_t per = (nviews + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = threadIdx.x * per, e = min(nviews, b + per);
+    uint32_t sum = 0;
+    for (uint32_t v = b; v < e; v++) sum += (counts[v] + chunk - 1u) / chunk;
+    // block exclusive scan of the per-thread sums
+    uint32_t incl = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < warp; w++) woff += s_part[w];
+    uint32_t run = woff + incl - sum;
+    for (uint32_t v = b; v < e; v++) {
+        s_prefix[v] = run;
+        run += (counts[v] + chunk - 1u) / chunk;
+    }
+    if (threadIdx.x == blockDim.x - 1) s_prefix[nviews] = woff + incl;
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) coarse_kernel(const CastParams p) {
+    __shared__ ViewConst s_vc;
+    __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
+    __shared__ uint32_t s_woff[8];
+    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_ticket;
+    build_chunk_prefix(p.qcount + p.view_base, p.nviews, s_prefix);
+    const uint32_t total = s_prefix[p.nviews];
+    uint32_t cur_view = 0xFFFFFFFFu;
+    uint32_t vl = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s_ticket = atomicAdd(p.tickets + 0, 1u);
+        __syncthreads();
+        const uint32_t g = s_ticket;
+        if (g >= total) break;
+        while (s_prefix[vl + 1] <= g) vl++;  // tickets grow monotonically within a block: amortised O(1)
+        const uint32_t view = vl + p.view_base;
+        if (view != cur_view) {
+            __syncthreads();
+            load_view_const(s_vc, p.views + view);
+            cur_view = view;
+        }
+        const ViewConst& vc = s_vc;
+        const uint32_t count = p.qcount[view];
+        const uint32_t idx = (g - s_prefix[vl]) * 256u + threadIdx.x;
+        bool keep = false;
+        uint32_t pid = 0;
+        if (idx < count) {
+            pid = p.queue[(size_t)view * p.queue_cap + idx];
+            const int py = (int)(pid >> 16), px = (int)(pid & 0xFFFFu);
+            if (!(vc.flags & kViewFastOk)) {
+                keep = true;
+            } else {
+                float dx, dy, dz;
+                ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
+                keep = !coarse_miss(p.map, vc, dx, dy, dz);
+            }
+            if (!keep && p.pix_hit) {
+                const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
+                p.pix_hit[o] = kNone;
+                if (p.pix_depth) p.pix_depth[o] = 0.0f;
+            }
+        }
+        block_append(keep, pid, p.queue2 + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
+    }
+}
+
+// 64-thread blocks (= 64-ray chunks) measured best: 256 -> 128 -> 64 gains 2-4 % (less time behind the slowest warp of a
+// chunk); 48 registers / 20 blocks per SM beats 40 registers / 24 blocks and 32 / 32 (spills) by 3-8 %.
+constexpr int kMarchBlock = 64, kMarchMinBlocks = 20;
+template <int BS, int MINB>
+__global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
+    __shared__ ViewConst s_vc;
+    __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
+    __shared__ uint32_t s_ticket;
+    build_chunk_prefix(p.qcount2 + p.view_base, p.nviews, s_prefix);
+    const uint32_t total = s_prefix[p.nviews];
+    uint32_t cur_view = 0xFFFFFFFFu;
+    uint32_t c_probes = 0, c_hits = 0, c_steps = 0;
+    uint32_t vl = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s_ticket = atomicAdd(p.tickets + 1, 1u);
+        __syncthreads();
+        const uint32_t g = s_ticket;
+        __syncthreads();
+        if (g >= total) break;
+        while (s_prefix[vl + 1] <= g) vl++;  // tickets grow monotonically within a block: amortised O(1)
+        const uint32_t view = vl + p.view_base;
+        if (view != cur_view) {
+            if (cur_view != 0xFFFFFFFFu) {  // flush the finished view's counters
+                commit_stats(p.stats + 4 * (size_t)cur_view, 0u, c_probes, c_hits, c_steps);
+                c_probes = c_hits = c_steps = 0;
+            }
+            __syncthreads();
+            load_view_const(s_vc, p.views + view);
+            cur_view = view;
+        }
+        const ViewConst& vc = s_vc;
+        const uint32_t count = p.qcount2[view];
+        const uint32_t idx = (g - s_prefix[vl]) * (uint32_t)BS + threadIdx.x;
+        if (idx < count) {
+            const uint32_t packed = p.queue2[(size_t)view * p.queue_cap + idx];
+            const int py = (int)(packed >> 16), px = (int)(packed & 0xFFFFu);
+            const uint32_t pid = (uint32_t)py * (uint32_t)p.GW + (uint32_t)px;
+            CastResult res;
+            res.rank = kNone;
+            res.steps = 0;
+            res.probes = 0;
+            res.k0 = res.k1 = res.k2 = 0;
+            RayState r;
+            float dx, dy, dz;
+            ray_direction(p.cam, vc, px, py, dx, dy, dz);
+            if (ray_init(vc, p.map.resolution, dx, dy, dz, r)) {
+                if (!(vc.flags & kViewFastOk))
+                    march_plain(p.map, p.cam, vc, r, res);
+                else
+                    march_axis(p.map, vc, r, res);
+            }
+            write_hit(p, vc, view, pid, res);
+            c_probes += res.probes;
+            c_hits += res.rank != kNone ? 1u : 0u;
+            c_steps += res.steps;
+        }
+    }
+    if (cur_view != 0xFFFFFFFFu) commit_stats(p.stats + 4 * (size_t)cur_view, 0u, c_probes, c_hits, c_steps);
+}
+
+// ---- PLAIN / FAST variants: one kernel, one thread per pixel of a 32x8 tile ----------------------------------------
+template <int VARIANT, bool MASKED>
+__global__ void __launch_bounds__(256) raycast_kernel(const CastParams p) {
+    __shared__ ViewConst s_vc;
+    const uint32_t view = blockIdx.y + p.view_base;
+    load_view_const(s_vc, p.views + view);
+    const ViewConst& vc = s_vc;
+    const int tiles_x = (p.GW + 31) >> 5;
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int px = (tile_x << 5) + ((warp & 3) << 3) + (lane & 7);
+    const int py = (tile_y << 3) + ((warp >> 2) << 2) + (lane >> 3);
+    const bool in_grid = px < p.GW && py < p.GH;
+    const unsigned long long pid = (unsigned long long)py * p.GW + px;
+    bool active = in_grid && (vc.flags & kViewInMap) && !(vc.flags & kViewInObject);
+    if (MASKED && active) {
+        const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
+        active = (w >> (pid & 31)) & 1u;
+    }
+    CastResult res;
+    res.rank = kNone;
+    res.steps = 0;
+    res.probes = 0;
+    res.k0 = res.k1 = res.k2 = 0;
+    if (active) {
+        RayState r;
+        const bool plain = VARIANT == PRV_VARIANT_PLAIN || !(vc.flags & kViewFastOk);
+        if (setup_ray(p.cam, vc, p.map.resolution, px, py, r)) {
+            if (plain)
+                march_plain(p.map, p.cam, vc, r, res);
+            else
+                march_fast(p.map, vc, r, res);
+        }
+    }
+    if (in_grid && (!MASKED || active)) write_hit(p, vc, view, pid, res);
+    commit_stats(p.stats + 4 * (size_t)view, active ? 1u : 0u, res.probes, res.rank != kNone ? 1u : 0u, res.steps);
+}
+
+// voxel-driven mode, stage 1 (main.cpp:243-251 of the reference): project every occupied voxel centre, mark its
+// TRUNCATED pixel in the (W+1)x(H+1) mask (pixel == W or == H passes the reference's '>' test).
+__global__ void __launch_bounds__(256) project_voxels_kernel(DevMap map, DevCam cam, const ViewConst* views, uint32_t view_base,
+                                                             uint32_t* mask, uint32_t mask_words, uint32_t* voxel_pix) {
+    const uint32_t view = blockIdx.y + view_base;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= map.n_occ) return;
+    const ViewConst& vc = views[view];
+    uint32_t pid = kNone;
+    if ((vc.flags & kViewInMap) && !(vc.flags & kViewInObject)) {
+        const float ex = (float)key_to_coord_d(map.keys[3 * i + 0], map.resolution);
+        const float ey = (float)key_to_coord_d(map.keys[3 * i + 1], map.resolution);
+        const float ez = (float)key_to_coord_d(map.keys[3 * i + 2], map.resolution);
+        const float vx = (float)row_apply(vc.inv + 0, (double)ex, (double)ey, (double)ez);
+        const float vy = (float)row_apply(vc.inv + 4, (double)ex, (double)ey, (double)ez);
+        const float vz = (float)row_apply(vc.inv + 8, (double)ex, (double)ey, (double)ez);
+        float u, v;
+        project_point_to_pixel(cam, vx, vy, vz, u, v);
+        // reject: pixel<0 || pixel>W (resp. H); NaN is rejected too (float->int of NaN is UB in the reference)
+        if (u >= 0.0f && u <= (float)cam.W && v >= 0.0f && v <= (float)cam.H) {
+            const int ix = (int)u, iy = (int)v;  // truncation at the int-parameter call, main.cpp:253
+            pid = (uint32_t)iy * (uint32_t)(cam.W + 1) + (uint32_t)ix;
+            atomicOr(mask + (size_t)view * mask_words + (pid >> 5), 1u << (pid & 31));
+        }
+    }
+    voxel_pix[(size_t)view * map.n_occ + i] = pid;
+}
+
+// voxel-driven mode, stage 3: voxel i takes the result of its pixel's ray
+__global__ void __launch_bounds__(256) gather_voxel_hits_kernel(uint32_t n_occ, const uint32_t* voxel_pix, const uint32_t* pix_hit,
+                                                                unsigned long long pix_stride, uint32_t* out) {
+    const uint32_t view = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_occ) return;
+    const uint32_t pid = voxel_pix[(size_t)view * n_occ + i];
+    out[(size_t)view * n_occ + i] = pid == kNone ? kNone : pix_hit[(size_t)view * pix_stride + pid];
+}
+
+// cloud->points image of Perception_3D::precept for one view (main.cpp:240-283)
+__global__ void __launch_bounds__(256) precept_points_kernel(DevMap map, const uint32_t* voxel_hit, prv_point_xyzrgb* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= map.n_occ) return;
+    prv_point_xyzrgb pt;
+    pt.x = pt.y = pt.z = 0.0f;
+    pt.w = 1.0f;
+    pt.b = pt.g = pt.r = 0;
+    pt.a = 255;
+    pt.pad[0] = pt.pad[1] = pt.pad[2] = 0.0f;
+    const uint32_t h = voxel_hit[i];
+    if (h != kNone) {
+        pt.x = (float)key_to_coord_d(map.keys[3 * h + 0], map.resolution);
+        pt.y = (float)key_to_coord_d(map.keys[3 * h + 1], map.resolution);
+        pt.z = (float)key_to_coord_d(map.keys[3 * h + 2], map.resolution);
+        pt.r = map.rgb[3 * h + 0];
+        pt.g = map.rgb[3 * h + 1];
+        pt.b = map.rgb[3 * h + 2];
+    }
+    out[i] = pt;
+}

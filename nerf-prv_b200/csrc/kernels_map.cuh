@@ -1,0 +1,142 @@
+// kernels_map.cuh -- GPU map build (bitmaps, coarse grid, prefix, rank table) and GPU ingest of the cloud
+// Part of the single translation unit prv_device.cu (included there, in order); see DESIGN.md section 4.
+#pragma once
+
+// ground-truth map build on the GPU (replaces the CPU octree insertion as far as the cast needs it) ------------------
+struct MapBuild {
+    int lo[3], n[3], wx, row_log2, nc[3];
+    uint32_t n_occ;
+    unsigned long long slack_bits, nwords;
+    uint32_t* bitmap;
+    uint32_t* pad;
+    uint32_t* coarse;
+    uint32_t* prefix;
+    uint32_t* leaf_of_raster;
+    const uint16_t* keys;
+};
+
+// per occupied voxel: occupancy bit, padded-bitmap bit, and the (<= 8) coarse cells within one voxel of it
+__global__ void __launch_bounds__(256) map_scatter_kernel(MapBuild b) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n_occ) return;
+    const int q0 = b.keys[3 * i] - b.lo[0], q1 = b.keys[3 * i + 1] - b.lo[1], q2 = b.keys[3 * i + 2] - b.lo[2];
+    atomicOr(b.bitmap + ((size_t)(q2 * b.n[1] + q1) * b.wx + (q0 >> 5)), 1u << (q0 & 31));
+    const unsigned long long L = b.slack_bits + ((unsigned long long)((q2 + 1) * (b.n[1] + 2) + (q1 + 1)) << b.row_log2) + (unsigned long long)(q0 + 1);
+    atomicOr(b.pad + (L >> 5), 1u << (L & 31));
+    const int q[3] = {q0, q1, q2};
+    int cl[3], ch[3];
+    for (int a = 0; a < 3; a++) {
+        cl[a] = max(0, (q[a] - 1) / kCoarse);
+        ch[a] = min(b.nc[a] - 1, (q[a] + 1) / kCoarse);
+    }
+    for (int K = cl[2]; K <= ch[2]; K++)
+        for (int J = cl[1]; J <= ch[1]; J++)
+            for (int I = cl[0]; I <= ch[0]; I++) {
+                const uint32_t c = (uint32_t)((K * b.nc[1] + J) * b.nc[0] + I);
+                atomicOr(b.coarse + (c >> 5), 1u << (c & 31));
+            }
+}
+
+// the fully-set one-voxel shell of the padded bitmap: one thread per padded row
+__global__ void __launch_bounds__(256) map_shell_kernel(MapBuild b) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n1p = (uint32_t)b.n[1] + 2, n2p = (uint32_t)b.n[2] + 2;
+    if (row >= n1p * n2p) return;
+    const uint32_t c1 = row % n1p, c2 = row / n1p;
+    const unsigned long long L0 = b.slack_bits + ((unsigned long long)row << b.row_log2);  // multiple of 32
+    uint32_t* w = b.pad + (L0 >> 5);
+    const uint32_t last = (uint32_t)b.n[0] + 1;  // padded x of the far shell cell
+    if (c1 == 0 || c1 == n1p - 1 || c2 == 0 || c2 == n2p - 1) {
+        for (uint32_t x = 0; x <= last; x += 32) {
+            const uint32_t cnt = min(32u, last + 1 - x);
+            atomicOr(w + (x >> 5), cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u));
+        }
+    } else {
+        atomicOr(w, 1u);
+        atomicOr(w + (last >> 5), 1u << (last & 31));
+    }
+}
+
+// exclusive popcount prefix over the occupancy words: one block, each thread a contiguous run
+__global__ void __launch_bounds__(1024) map_prefix_kernel(MapBuild b) {
+    __shared__ uint32_t s_warp[32];
+    const unsigned long long per = (b.nwords + blockDim.x - 1) / blockDim.x;
+    const unsigned long long beg = min(b.nwords, threadIdx.x * per), end = min(b.nwords, beg + per);
+    uint32_t sum = 0;
+    for (unsigned long long w = beg; w < end; w++) sum += __popc(b.bitmap[w]);
+    uint32_t incl = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = s_warp[lane], iv = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, iv, o);
+            if (lane >= o) iv += t;
+        }
+        s_warp[lane] = iv - v;
+    }
+    __syncthreads();
+    uint32_t run = s_warp[warp] + incl - sum;
+    for (unsigned long long w = beg; w < end; w++) {
+        b.prefix[w] = run;
+        run += __popc(b.bitmap[w]);
+    }
+}
+
+// raster rank -> leaf rank
+__global__ void __launch_bounds__(256) map_rank_kernel(MapBuild b) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b.n_occ) return;
+    const int q0 = b.keys[3 * i] - b.lo[0], q1 = b.keys[3 * i + 1] - b.lo[1], q2 = b.keys[3 * i + 2] - b.lo[2];
+    const size_t w = (size_t)(q2 * b.n[1] + q1) * b.wx + (q0 >> 5);
+    b.leaf_of_raster[b.prefix[w] + __popc(b.bitmap[w] & ((1u << (q0 & 31)) - 1u))] = i;
+}
+
+// GPU ingest: cloud points -> leaf-ordered unique keys + first-point colours ------------------------
+// key = (int)floor(resolution_factor * (double)coord) + 32768 (coordToKeyChecked, main.cpp:1015), invalid points sort last
+__global__ void __launch_bounds__(256) ingest_keys_kernel(const float* __restrict__ xyz, uint32_t P, double resolution_factor,
+                                                          unsigned long long* __restrict__ codes, uint32_t* __restrict__ index) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    uint16_t k[3];
+    bool ok = true;
+    for (int a = 0; a < 3; a++) {
+        const int scaled = (int)floor(prvk::dmul(resolution_factor, (double)xyz[3 * (size_t)i + a])) + prv::kTreeMaxVal;
+        ok = ok && scaled >= 0 && scaled < 2 * prv::kTreeMaxVal;
+        k[a] = (uint16_t)scaled;
+    }
+    codes[i] = ok ? prv::morton_code(k[0], k[1], k[2]) : (1ull << 48);
+    index[i] = i;
+}
+
+// head[i] = 1 when sorted entry i starts a new voxel (head[P] = 0 pads the scan so pos[P] = number of voxels)
+__global__ void __launch_bounds__(256) ingest_heads_kernel(const unsigned long long* __restrict__ codes, uint32_t P, uint32_t* __restrict__ head) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > P) return;
+    uint32_t h = 0;
+    if (i < P) {
+        const unsigned long long c = codes[i];
+        h = (c < (1ull << 48)) && (i == 0 || codes[i - 1] != c) ? 1u : 0u;
+    }
+    head[i] = h;
+}
+
+__global__ void __launch_bounds__(256) ingest_compact_kernel(const unsigned long long* __restrict__ codes, const uint32_t* __restrict__ index,
+                                                             const uint32_t* __restrict__ head, const uint32_t* __restrict__ pos, uint32_t P,
+                                                             const uint8_t* __restrict__ rgb_in, uint16_t* __restrict__ keys_out, uint8_t* __restrict__ rgb_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P || !head[i]) return;
+    const uint32_t j = pos[i];
+    uint16_t k[3];
+    prv::morton_decode(codes[i], k);
+    const uint32_t src = index[i];
+    for (int a = 0; a < 3; a++) {
+        keys_out[3 * (size_t)j + a] = k[a];
+        rgb_out[3 * (size_t)j + a] = rgb_in[3 * (size_t)src + a];
+    }
+}

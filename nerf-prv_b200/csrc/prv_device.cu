@@ -25,952 +25,12 @@ using namespace prvk;
 // kernels
 // =====================================================================================================
 
-// deterministic counters, one set per view: block-reduce, then one atomic per counter per block (per-warp atomics on
-// one address serialise in L2 and were measured to bound the whole kernel)
-__device__ __forceinline__ void commit_stats(unsigned long long* view_stats, uint32_t rays, uint32_t probes, uint32_t hits, uint32_t steps) {
-    __shared__ uint32_t s_cnt[4][8];
-    uint32_t c[4] = {rays, probes, hits, steps};
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-        for (int o = 16; o > 0; o >>= 1) c[i] += __shfl_down_sync(0xFFFFFFFFu, c[i], o);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0)
-        for (int i = 0; i < 4; i++) s_cnt[i][warp] = c[i];
-    __syncthreads();
-    if (threadIdx.x < 4) {
-        unsigned long long t = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_cnt[threadIdx.x][w];
-        if (t) atomicAdd(view_stats + threadIdx.x, t);
-    }
-}
-
-__device__ __forceinline__ void load_view_const(ViewConst& dst, const ViewConst* src) {
-    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
-    uint32_t* d32 = reinterpret_cast<uint32_t*>(&dst);
-    for (int i = threadIdx.x; i < (int)(sizeof(ViewConst) / 4); i += blockDim.x) d32[i] = s32[i];
-    __syncthreads();
-}
-
-__device__ __forceinline__ void write_hit(const CastParams& p, const ViewConst& vc, uint32_t view, unsigned long long pid, const CastResult& res) {
-    if (res.rank != kNone) {
-        uint32_t* row = p.bitsets32 + (size_t)view * (2u * p.map.words64);
-        const uint32_t bit = 1u << (res.rank & 31);
-        uint32_t* w = row + (res.rank >> 5);
-        if (!(*reinterpret_cast<volatile uint32_t*>(w) & bit)) atomicOr(w, bit);
-    }
-    if (p.pix_hit) {
-        p.pix_hit[(size_t)view * p.pix_stride + pid] = res.rank;
-        if (p.pix_depth) {
-            float d = 0.0f;
-            if (res.rank != kNone) d = (float)__dsqrt_rn(dist_sq_at(vc, p.map.resolution, res.k0, res.k1, res.k2));
-            p.pix_depth[(size_t)view * p.pix_stride + pid] = d;
-        }
-    }
-}
-
-// ---- AXIS pipeline ------------------------------------------------------------------------------------------------
-// kernel 1 (cull_kernel):   every pixel, loose float slab test against the grown AABB; survivors -> queue 1
-// kernel 2 (coarse_kernel): dense warps over queue 1, conservative coarse-brick walk; survivors -> queue 2
-// kernel 3 (march_kernel):  dense warps over queue 2, the exact castRay march
-// Kernels 2 and 3 run persistent blocks that pull 256-ray chunks of a flattened (view, chunk) list with an atomic
-// ticket, so expensive and cheap chunks balance across the 148 SMs and there is no partial last wave.
-
-// block-level stream compaction of `keep` lanes into a per-view queue: one atomic per block
-__device__ __forceinline__ void block_append(bool keep, uint32_t value, uint32_t* queue_view, uint32_t* count_view, uint32_t* s_woff, uint32_t* s_base) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
-    if (lane == 0) s_woff[warp] = __popc(bal);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int w = 0; w < 8; w++) {
-            const uint32_t c = s_woff[w];
-            s_woff[w] = tot;
-            tot += c;
-        }
-        *s_base = tot ? atomicAdd(count_view, tot) : 0u;
-    }
-    __syncthreads();
-    if (keep) queue_view[*s_base + s_woff[warp] + __popc(bal & ((1u << lane) - 1u))] = value;
-    __syncthreads();  // s_woff / s_base are reused by the next chunk
-}
-
-// One block per 32x32 pixel region of one view (blockIdx.x = region, blockIdx.y = view); every thread owns 4 pixels,
-// one in each 32x8 row-tile (a warp covers an 8x4 patch per row-tile).
-// Region test: the region's rays lie inside the cone around the mean corner direction whose half-angle is the largest
-// corner angle (the pixel->direction map is projective up to the mild, host-checked lens distortion, for which the
-// corners are taken 2 pixels outside the region); if that cone misses the bounding sphere of the grown AABB, no ray
-// of the region can touch the AABB and the per-pixel tests are skipped.
-template <bool MASKED>
-__global__ void __launch_bounds__(256) cull_kernel(const CastParams p) {
-    __shared__ ViewConst s_vc;
-    __shared__ uint32_t s_woff[4][8];
-    __shared__ uint32_t s_base;
-    __shared__ uint32_t s_rays[8];
-    __shared__ int s_skip;
-    const uint32_t view = blockIdx.y + p.view_base;
-    load_view_const(s_vc, p.views + view);
-    const ViewConst& vc = s_vc;
-    const int regions_x = (p.GW + 31) >> 5;
-    const int region_x = blockIdx.x % regions_x, region_y = blockIdx.x / regions_x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool view_ok = (vc.flags & kViewInMap) && !(vc.flags & kViewInObject);
-    const bool fast = (vc.flags & kViewFastOk) != 0;
-
-    if (threadIdx.x < 32) {
-        // Region test (warp 0): the region's rays lie inside the pyramid spanned by the four corner rays taken 2 px
-        // outside the region (the pixel->direction map is affine up to the lens distortion, whose deviation inside any
-        // region was verified on the host to stay within that margin).  If all eight corners of the AABB grown by
-        // 2 voxels lie outside one side plane of the pyramid, no ray of the region can touch the AABB.
-        // lane = plane (0..3) * 8 + box corner (0..7): 32 dot products, one ballot.
-        bool skip = false;
-        if (!MASKED && view_ok && fast && p.cam.region_cull_ok) {
-            const int plane = lane >> 3, corner = lane & 7;
-            // pyramid corners counter-clockwise in pixel space: (x0,y0) (x1,y0) (x1,y1) (x0,y1)
-            const float x0 = (float)((region_x << 5) - 2), x1 = (float)((region_x << 5) + 33);
-            const float y0 = (float)((region_y << 5) - 2), y1 = (float)((region_y << 5) + 33);
-            const float ax = (plane == 0 || plane == 3) ? x0 : x1, ay = (plane == 0 || plane == 1) ? y0 : y1;   // corner `plane`
-            const float bx = (plane == 0 || plane == 1) ? x1 : x0, by = (plane == 1 || plane == 2) ? y1 : y0;   // corner `plane+1`
-            float adx, ady, adz, bdx, bdy, bdz, cdx, cdy, cdz;
-            ray_direction_approx(p.cam, vc, ax, ay, adx, ady, adz);
-            ray_direction_approx(p.cam, vc, bx, by, bdx, bdy, bdz);
-            ray_direction_approx(p.cam, vc, 0.5f * (x0 + x1), 0.5f * (y0 + y1), cdx, cdy, cdz);  // interior reference ray
-            // plane through the origin containing corner rays a and b; orient the normal away from the interior ray
-            float nx = ady * bdz - adz * bdy, ny = adz * bdx - adx * bdz, nz = adx * bdy - ady * bdx;
-            const float sgn = (nx * cdx + ny * cdy + nz * cdz) > 0.0f ? -1.0f : 1.0f;
-            nx *= sgn; ny *= sgn; nz *= sgn;
-            const float inv_n = rsqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
-            const float px = ((corner & 1) ? p.map.bmax[0] : p.map.bmin[0]) - vc.origin[0];
-            const float py = ((corner & 2) ? p.map.bmax[1] : p.map.bmin[1]) - vc.origin[1];
-            const float pz = ((corner & 4) ? p.map.bmax[2] : p.map.bmin[2]) - vc.origin[2];
-            const float dist = fmaf(nx, px, fmaf(ny, py, nz * pz)) * inv_n;  // signed distance of the box corner to the plane
-            const bool outside = dist > 1.0e-5f;                             // float error here is ~1e-7 m
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, outside);
-            skip = ((bal & 0xFFu) == 0xFFu) || ((bal & 0xFF00u) == 0xFF00u) || ((bal & 0xFF0000u) == 0xFF0000u) || ((bal & 0xFF000000u) == 0xFF000000u);
-        }
-        if (lane == 0) s_skip = skip ? 1 : 0;
-    }
-    __syncthreads();
-    if (s_skip != 0) {
-        // the whole region provably misses: record "no hit" for its pixels and leave (no compaction protocol)
-        if (p.pix_hit) {
-            const int px = (region_x << 5) + ((warp & 3) << 3) + (lane & 7);
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
-                if (px < p.GW && py < p.GH) {
-                    const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
-                    p.pix_hit[o] = kNone;
-                    if (p.pix_depth) p.pix_depth[o] = 0.0f;
-                }
-            }
-        }
-        if (threadIdx.x == 0) {
-            const int w = min(32, p.GW - (region_x << 5)), h = min(32, p.GH - (region_y << 5));
-            atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)(w * h));
-        }
-        return;
-    }
-    const bool skip = false;
-
-    uint32_t keep_mask = 0;  // bit t: this thread's pixel in row-tile t survives
-    uint32_t pids[4];
-    uint32_t nrays = 0;
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        const int px = (region_x << 5) + ((warp & 3) << 3) + (lane & 7);
-        const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
-        const bool in_grid = px < p.GW && py < p.GH;
-        const unsigned long long pid = (unsigned long long)py * p.GW + px;
-        pids[t] = ((uint32_t)py << 16) | (uint32_t)px;  // queues carry (y,x) packed: no division downstream
-        bool active = in_grid && view_ok;
-        if (MASKED && active) {
-            const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
-            active = (w >> (pid & 31)) & 1u;
-        }
-        bool survive = false;
-        if (active && !skip) {
-            if (!fast) {
-                survive = true;  // this view needs the literal march (max-range test): no cull
-            } else {
-                float dx, dy, dz;
-                ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
-                survive = !loose_miss(p.map, vc, dx, dy, dz);
-            }
-        }
-        if (in_grid && !survive && p.pix_hit && (!MASKED || active)) {
-            p.pix_hit[(size_t)view * p.pix_stride + pid] = kNone;
-            if (p.pix_depth) p.pix_depth[(size_t)view * p.pix_stride + pid] = 0.0f;
-        }
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, survive);
-        nrays += __popc(__ballot_sync(0xFFFFFFFFu, active));
-        if (survive) keep_mask |= 1u << t;
-        if (lane == 0) s_woff[t][warp] = __popc(bal);
-        // lane-local rank within the warp for this row-tile, kept in the high bits
-        keep_mask |= (uint32_t)__popc(bal & ((1u << lane) - 1u)) << (8 + 6 * t);
-    }
-    if (lane == 0) s_rays[warp] = nrays;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0, rays = 0;
-        for (int t = 0; t < 4; t++)
-            for (int w = 0; w < 8; w++) {
-                const uint32_t c = s_woff[t][w];
-                s_woff[t][w] = tot;
-                tot += c;
-            }
-        for (int w = 0; w < 8; w++) rays += s_rays[w];
-        s_base = tot ? atomicAdd(p.qcount + view, tot) : 0u;
-        if (rays) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)rays);
-    }
-    __syncthreads();
-    if (keep_mask & 0xFu) {
-        uint32_t* q = p.queue + (size_t)view * p.queue_cap + s_base;
-#pragma unroll
-        for (int t = 0; t < 4; t++)
-            if (keep_mask & (1u << t)) q[s_woff[t][warp] + ((keep_mask >> (8 + 6 * t)) & 63u)] = pids[t];
-    }
-}
-
-// exclusive prefix of chunk counts (chunk = blockDim.x rays) over the views of this launch -> s_prefix[0..nviews]
-__device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint32_t nviews, uint32_t* s_prefix) {
-    const uint32_t chunk = blockDim.x;
-    __shared__ uint32_t s_part[8];
-    // each thread owns a contiguous run of views
-    const uint32_t per = (nviews + blockDim.x - 1) / blockDim.x;
-    const uint32_t b = threadIdx.x * per, e = min(nviews, b + per);
-    uint32_t sum = 0;
-    for (uint32_t v = b; v < e; v++) sum += (counts[v] + chunk - 1u) / chunk;
-    // block exclusive scan of the per-thread sums
-    uint32_t incl = sum;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_part[warp] = incl;
-    __syncthreads();
-    uint32_t woff = 0;
-    for (int w = 0; w < warp; w++) woff += s_part[w];
-    uint32_t run = woff + incl - sum;
-    for (uint32_t v = b; v < e; v++) {
-        s_prefix[v] = run;
-        run += (counts[v] + chunk - 1u) / chunk;
-    }
-    if (threadIdx.x == blockDim.x - 1) s_prefix[nviews] = woff + incl;
-    __syncthreads();
-}
-
-__global__ void __launch_bounds__(256) coarse_kernel(const CastParams p) {
-    __shared__ ViewConst s_vc;
-    __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
-    __shared__ uint32_t s_woff[8];
-    __shared__ uint32_t s_base;
-    __shared__ uint32_t s_ticket;
-    build_chunk_prefix(p.qcount + p.view_base, p.nviews, s_prefix);
-    const uint32_t total = s_prefix[p.nviews];
-    uint32_t cur_view = 0xFFFFFFFFu;
-    uint32_t vl = 0;
-    for (;;) {
-        if (threadIdx.x == 0) s_ticket = atomicAdd(p.tickets + 0, 1u);
-        __syncthreads();
-        const uint32_t g = s_ticket;
-        if (g >= total) break;
-        while (s_prefix[vl + 1] <= g) vl++;  // tickets grow monotonically within a block: amortised O(1)
-        const uint32_t view = vl + p.view_base;
-        if (view != cur_view) {
-            __syncthreads();
-            load_view_const(s_vc, p.views + view);
-            cur_view = view;
-        }
-        const ViewConst& vc = s_vc;
-        const uint32_t count = p.qcount[view];
-        const uint32_t idx = (g - s_prefix[vl]) * 256u + threadIdx.x;
-        bool keep = false;
-        uint32_t pid = 0;
-        if (idx < count) {
-            pid = p.queue[(size_t)view * p.queue_cap + idx];
-            const int py = (int)(pid >> 16), px = (int)(pid & 0xFFFFu);
-            if (!(vc.flags & kViewFastOk)) {
-                keep = true;
-            } else {
-                float dx, dy, dz;
-                ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
-                keep = !coarse_miss(p.map, vc, dx, dy, dz);
-            }
-            if (!keep && p.pix_hit) {
-                const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
-                p.pix_hit[o] = kNone;
-                if (p.pix_depth) p.pix_depth[o] = 0.0f;
-            }
-        }
-        block_append(keep, pid, p.queue2 + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
-    }
-}
-
-// 64-thread blocks (= 64-ray chunks) measured best: 256 -> 128 -> 64 gains 2-4 % (less time behind the slowest warp of a
-// chunk); 48 registers / 20 blocks per SM beats 40 registers / 24 blocks and 32 / 32 (spills) by 3-8 %.
-constexpr int kMarchBlock = 64, kMarchMinBlocks = 20;
-template <int BS, int MINB>
-__global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
-    __shared__ ViewConst s_vc;
-    __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
-    __shared__ uint32_t s_ticket;
-    build_chunk_prefix(p.qcount2 + p.view_base, p.nviews, s_prefix);
-    const uint32_t total = s_prefix[p.nviews];
-    uint32_t cur_view = 0xFFFFFFFFu;
-    uint32_t c_probes = 0, c_hits = 0, c_steps = 0;
-    uint32_t vl = 0;
-    for (;;) {
-        if (threadIdx.x == 0) s_ticket = atomicAdd(p.tickets + 1, 1u);
-        __syncthreads();
-        const uint32_t g = s_ticket;
-        __syncthreads();
-        if (g >= total) break;
-        while (s_prefix[vl + 1] <= g) vl++;  // tickets grow monotonically within a block: amortised O(1)
-        const uint32_t view = vl + p.view_base;
-        if (view != cur_view) {
-            if (cur_view != 0xFFFFFFFFu) {  // flush the finished view's counters
-                commit_stats(p.stats + 4 * (size_t)cur_view, 0u, c_probes, c_hits, c_steps);
-                c_probes = c_hits = c_steps = 0;
-            }
-            __syncthreads();
-            load_view_const(s_vc, p.views + view);
-            cur_view = view;
-        }
-        const ViewConst& vc = s_vc;
-        const uint32_t count = p.qcount2[view];
-        const uint32_t idx = (g - s_prefix[vl]) * (uint32_t)BS + threadIdx.x;
-        if (idx < count) {
-            const uint32_t packed = p.queue2[(size_t)view * p.queue_cap + idx];
-            const int py = (int)(packed >> 16), px = (int)(packed & 0xFFFFu);
-            const uint32_t pid = (uint32_t)py * (uint32_t)p.GW + (uint32_t)px;
-            CastResult res;
-            res.rank = kNone;
-            res.steps = 0;
-            res.probes = 0;
-            res.k0 = res.k1 = res.k2 = 0;
-            RayState r;
-            float dx, dy, dz;
-            ray_direction(p.cam, vc, px, py, dx, dy, dz);
-            if (ray_init(vc, p.map.resolution, dx, dy, dz, r)) {
-                if (!(vc.flags & kViewFastOk))
-                    march_plain(p.map, p.cam, vc, r, res);
-                else
-                    march_axis(p.map, vc, r, res);
-            }
-            write_hit(p, vc, view, pid, res);
-            c_probes += res.probes;
-            c_hits += res.rank != kNone ? 1u : 0u;
-            c_steps += res.steps;
-        }
-    }
-    if (cur_view != 0xFFFFFFFFu) commit_stats(p.stats + 4 * (size_t)cur_view, 0u, c_probes, c_hits, c_steps);
-}
-
-// ---- PLAIN / FAST variants: one kernel, one thread per pixel of a 32x8 tile ----------------------------------------
-template <int VARIANT, bool MASKED>
-__global__ void __launch_bounds__(256) raycast_kernel(const CastParams p) {
-    __shared__ ViewConst s_vc;
-    const uint32_t view = blockIdx.y + p.view_base;
-    load_view_const(s_vc, p.views + view);
-    const ViewConst& vc = s_vc;
-    const int tiles_x = (p.GW + 31) >> 5;
-    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int px = (tile_x << 5) + ((warp & 3) << 3) + (lane & 7);
-    const int py = (tile_y << 3) + ((warp >> 2) << 2) + (lane >> 3);
-    const bool in_grid = px < p.GW && py < p.GH;
-    const unsigned long long pid = (unsigned long long)py * p.GW + px;
-    bool active = in_grid && (vc.flags & kViewInMap) && !(vc.flags & kViewInObject);
-    if (MASKED && active) {
-        const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
-        active = (w >> (pid & 31)) & 1u;
-    }
-    CastResult res;
-    res.rank = kNone;
-    res.steps = 0;
-    res.probes = 0;
-    res.k0 = res.k1 = res.k2 = 0;
-    if (active) {
-        RayState r;
-        const bool plain = VARIANT == PRV_VARIANT_PLAIN || !(vc.flags & kViewFastOk);
-        if (setup_ray(p.cam, vc, p.map.resolution, px, py, r)) {
-            if (plain)
-                march_plain(p.map, p.cam, vc, r, res);
-            else
-                march_fast(p.map, vc, r, res);
-        }
-    }
-    if (in_grid && (!MASKED || active)) write_hit(p, vc, view, pid, res);
-    commit_stats(p.stats + 4 * (size_t)view, active ? 1u : 0u, res.probes, res.rank != kNone ? 1u : 0u, res.steps);
-}
-
-// voxel-driven mode, stage 1 (main.cpp:243-251 of the reference): project every occupied voxel centre, mark its
-// TRUNCATED pixel in the (W+1)x(H+1) mask (pixel == W or == H passes the reference's '>' test).
-__global__ void __launch_bounds__(256) project_voxels_kernel(DevMap map, DevCam cam, const ViewConst* views, uint32_t view_base,
-                                                             uint32_t* mask, uint32_t mask_words, uint32_t* voxel_pix) {
-    const uint32_t view = blockIdx.y + view_base;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= map.n_occ) return;
-    const ViewConst& vc = views[view];
-    uint32_t pid = kNone;
-    if ((vc.flags & kViewInMap) && !(vc.flags & kViewInObject)) {
-        const float ex = (float)key_to_coord_d(map.keys[3 * i + 0], map.resolution);
-        const float ey = (float)key_to_coord_d(map.keys[3 * i + 1], map.resolution);
-        const float ez = (float)key_to_coord_d(map.keys[3 * i + 2], map.resolution);
-        const float vx = (float)row_apply(vc.inv + 0, (double)ex, (double)ey, (double)ez);
-        const float vy = (float)row_apply(vc.inv + 4, (double)ex, (double)ey, (double)ez);
-        const float vz = (float)row_apply(vc.inv + 8, (double)ex, (double)ey, (double)ez);
-        float u, v;
-        project_point_to_pixel(cam, vx, vy, vz, u, v);
-        // reject: pixel<0 || pixel>W (resp. H); NaN is rejected too (float->int of NaN is UB in the reference)
-        if (u >= 0.0f && u <= (float)cam.W && v >= 0.0f && v <= (float)cam.H) {
-            const int ix = (int)u, iy = (int)v;  // truncation at the int-parameter call, main.cpp:253
-            pid = (uint32_t)iy * (uint32_t)(cam.W + 1) + (uint32_t)ix;
-            atomicOr(mask + (size_t)view * mask_words + (pid >> 5), 1u << (pid & 31));
-        }
-    }
-    voxel_pix[(size_t)view * map.n_occ + i] = pid;
-}
-
-// voxel-driven mode, stage 3: voxel i takes the result of its pixel's ray
-__global__ void __launch_bounds__(256) gather_voxel_hits_kernel(uint32_t n_occ, const uint32_t* voxel_pix, const uint32_t* pix_hit,
-                                                                unsigned long long pix_stride, uint32_t* out) {
-    const uint32_t view = blockIdx.y;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_occ) return;
-    const uint32_t pid = voxel_pix[(size_t)view * n_occ + i];
-    out[(size_t)view * n_occ + i] = pid == kNone ? kNone : pix_hit[(size_t)view * pix_stride + pid];
-}
-
-// cloud->points image of Perception_3D::precept for one view (main.cpp:240-283)
-__global__ void __launch_bounds__(256) precept_points_kernel(DevMap map, const uint32_t* voxel_hit, prv_point_xyzrgb* out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= map.n_occ) return;
-    prv_point_xyzrgb pt;
-    pt.x = pt.y = pt.z = 0.0f;
-    pt.w = 1.0f;
-    pt.b = pt.g = pt.r = 0;
-    pt.a = 255;
-    pt.pad[0] = pt.pad[1] = pt.pad[2] = 0.0f;
-    const uint32_t h = voxel_hit[i];
-    if (h != kNone) {
-        pt.x = (float)key_to_coord_d(map.keys[3 * h + 0], map.resolution);
-        pt.y = (float)key_to_coord_d(map.keys[3 * h + 1], map.resolution);
-        pt.z = (float)key_to_coord_d(map.keys[3 * h + 2], map.resolution);
-        pt.r = map.rgb[3 * h + 0];
-        pt.g = map.rgb[3 * h + 1];
-        pt.b = map.rgb[3 * h + 2];
-    }
-    out[i] = pt;
-}
-
-__device__ __forceinline__ uint32_t block_reduce_sum(uint32_t v, uint32_t* s_red) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    uint32_t t = 0;
-    if (threadIdx.x < 32) {
-        t = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0u;
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xFFFFFFFFu, t, o);
-    }
-    return t;  // valid in thread 0
-}
-
-// ground-truth map build on the GPU (replaces the CPU octree insertion as far as the cast needs it) ------------------
-struct MapBuild {
-    int lo[3], n[3], wx, row_log2, nc[3];
-    uint32_t n_occ;
-    unsigned long long slack_bits, nwords;
-    uint32_t* bitmap;
-    uint32_t* pad;
-    uint32_t* coarse;
-    uint32_t* prefix;
-    uint32_t* leaf_of_raster;
-    const uint16_t* keys;
-};
-
-// per occupied voxel: occupancy bit, padded-bitmap bit, and the (<= 8) coarse cells within one voxel of it
-__global__ void __launch_bounds__(256) map_scatter_kernel(MapBuild b) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= b.n_occ) return;
-    const int q0 = b.keys[3 * i] - b.lo[0], q1 = b.keys[3 * i + 1] - b.lo[1], q2 = b.keys[3 * i + 2] - b.lo[2];
-    atomicOr(b.bitmap + ((size_t)(q2 * b.n[1] + q1) * b.wx + (q0 >> 5)), 1u << (q0 & 31));
-    const unsigned long long L = b.slack_bits + ((unsigned long long)((q2 + 1) * (b.n[1] + 2) + (q1 + 1)) << b.row_log2) + (unsigned long long)(q0 + 1);
-    atomicOr(b.pad + (L >> 5), 1u << (L & 31));
-    const int q[3] = {q0, q1, q2};
-    int cl[3], ch[3];
-    for (int a = 0; a < 3; a++) {
-        cl[a] = max(0, (q[a] - 1) / kCoarse);
-        ch[a] = min(b.nc[a] - 1, (q[a] + 1) / kCoarse);
-    }
-    for (int K = cl[2]; K <= ch[2]; K++)
-        for (int J = cl[1]; J <= ch[1]; J++)
-            for (int I = cl[0]; I <= ch[0]; I++) {
-                const uint32_t c = (uint32_t)((K * b.nc[1] + J) * b.nc[0] + I);
-                atomicOr(b.coarse + (c >> 5), 1u << (c & 31));
-            }
-}
-
-// the fully-set one-voxel shell of the padded bitmap: one thread per padded row
-__global__ void __launch_bounds__(256) map_shell_kernel(MapBuild b) {
-    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n1p = (uint32_t)b.n[1] + 2, n2p = (uint32_t)b.n[2] + 2;
-    if (row >= n1p * n2p) return;
-    const uint32_t c1 = row % n1p, c2 = row / n1p;
-    const unsigned long long L0 = b.slack_bits + ((unsigned long long)row << b.row_log2);  // multiple of 32
-    uint32_t* w = b.pad + (L0 >> 5);
-    const uint32_t last = (uint32_t)b.n[0] + 1;  // padded x of the far shell cell
-    if (c1 == 0 || c1 == n1p - 1 || c2 == 0 || c2 == n2p - 1) {
-        for (uint32_t x = 0; x <= last; x += 32) {
-            const uint32_t cnt = min(32u, last + 1 - x);
-            atomicOr(w + (x >> 5), cnt == 32 ? 0xFFFFFFFFu : ((1u << cnt) - 1u));
-        }
-    } else {
-        atomicOr(w, 1u);
-        atomicOr(w + (last >> 5), 1u << (last & 31));
-    }
-}
-
-// exclusive popcount prefix over the occupancy words: one block, each thread a contiguous run
-__global__ void __launch_bounds__(1024) map_prefix_kernel(MapBuild b) {
-    __shared__ uint32_t s_warp[32];
-    const unsigned long long per = (b.nwords + blockDim.x - 1) / blockDim.x;
-    const unsigned long long beg = min(b.nwords, threadIdx.x * per), end = min(b.nwords, beg + per);
-    uint32_t sum = 0;
-    for (unsigned long long w = beg; w < end; w++) sum += __popc(b.bitmap[w]);
-    uint32_t incl = sum;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t v = s_warp[lane], iv = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, iv, o);
-            if (lane >= o) iv += t;
-        }
-        s_warp[lane] = iv - v;
-    }
-    __syncthreads();
-    uint32_t run = s_warp[warp] + incl - sum;
-    for (unsigned long long w = beg; w < end; w++) {
-        b.prefix[w] = run;
-        run += __popc(b.bitmap[w]);
-    }
-}
-
-// raster rank -> leaf rank
-__global__ void __launch_bounds__(256) map_rank_kernel(MapBuild b) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= b.n_occ) return;
-    const int q0 = b.keys[3 * i] - b.lo[0], q1 = b.keys[3 * i + 1] - b.lo[1], q2 = b.keys[3 * i + 2] - b.lo[2];
-    const size_t w = (size_t)(q2 * b.n[1] + q1) * b.wx + (q0 >> 5);
-    b.leaf_of_raster[b.prefix[w] + __popc(b.bitmap[w] & ((1u << (q0 & 31)) - 1u))] = i;
-}
-
-// GPU ingest: cloud points -> leaf-ordered unique keys + first-point colours ------------------------
-// key = (int)floor(resolution_factor * (double)coord) + 32768 (coordToKeyChecked, main.cpp:1015), invalid points sort last
-__global__ void __launch_bounds__(256) ingest_keys_kernel(const float* __restrict__ xyz, uint32_t P, double resolution_factor,
-                                                          unsigned long long* __restrict__ codes, uint32_t* __restrict__ index) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    uint16_t k[3];
-    bool ok = true;
-    for (int a = 0; a < 3; a++) {
-        const int scaled = (int)floor(prvk::dmul(resolution_factor, (double)xyz[3 * (size_t)i + a])) + prv::kTreeMaxVal;
-        ok = ok && scaled >= 0 && scaled < 2 * prv::kTreeMaxVal;
-        k[a] = (uint16_t)scaled;
-    }
-    codes[i] = ok ? prv::morton_code(k[0], k[1], k[2]) : (1ull << 48);
-    index[i] = i;
-}
-
-// head[i] = 1 when sorted entry i starts a new voxel (head[P] = 0 pads the scan so pos[P] = number of voxels)
-__global__ void __launch_bounds__(256) ingest_heads_kernel(const unsigned long long* __restrict__ codes, uint32_t P, uint32_t* __restrict__ head) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > P) return;
-    uint32_t h = 0;
-    if (i < P) {
-        const unsigned long long c = codes[i];
-        h = (c < (1ull << 48)) && (i == 0 || codes[i - 1] != c) ? 1u : 0u;
-    }
-    head[i] = h;
-}
-
-__global__ void __launch_bounds__(256) ingest_compact_kernel(const unsigned long long* __restrict__ codes, const uint32_t* __restrict__ index,
-                                                             const uint32_t* __restrict__ head, const uint32_t* __restrict__ pos, uint32_t P,
-                                                             const uint8_t* __restrict__ rgb_in, uint16_t* __restrict__ keys_out, uint8_t* __restrict__ rgb_out) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P || !head[i]) return;
-    const uint32_t j = pos[i];
-    uint16_t k[3];
-    prv::morton_decode(codes[i], k);
-    const uint32_t src = index[i];
-    for (int a = 0; a < 3; a++) {
-        keys_out[3 * (size_t)j + a] = k[a];
-        rgb_out[3 * (size_t)j + a] = rgb_in[3 * (size_t)src + a];
-    }
-}
-
-// coverage_count[v] = popcount(vis[v])
-__global__ void __launch_bounds__(256) popcount_rows_kernel(const uint64_t* rows, uint32_t words64, uint32_t* counts) {
-    __shared__ uint32_t s_red[8];
-    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(rows + (size_t)blockIdx.x * words64);
-    uint32_t c = 0;
-    for (uint32_t w = threadIdx.x; w < words64 / 2; w += blockDim.x) {
-        const ulonglong2 v = row[w];
-        c += __popcll(v.x) + __popcll(v.y);
-    }
-    const uint32_t t = block_reduce_sum(c, s_red);
-    if (threadIdx.x == 0) counts[blockIdx.x] = t;
-}
-
-// greedy set cover ---------------------------------------------------------------------------------
-// best[k] = max over views of (gain << 32) | (0xFFFFFFFF - view_id): largest gain, then LOWEST view id.
-__global__ void __launch_bounds__(256) greedy_init_kernel(const uint64_t* rows, uint32_t words64, uint32_t first_row, uint32_t first_id,
-                                                          unsigned long long* best) {
-    __shared__ uint32_t s_red[8];
-    const uint64_t* row = rows + (size_t)first_row * words64;
-    uint32_t c = 0;
-    for (uint32_t w = threadIdx.x; w < words64; w += blockDim.x) c += __popcll(row[w]);
-    const uint32_t t = block_reduce_sum(c, s_red);
-    if (threadIdx.x == 0) best[0] = ((unsigned long long)t << 32) | (unsigned long long)(0xFFFFFFFFu - first_id);
-}
-
-// iteration k >= 1: covered_k = covered_{k-1} | row[best_{k-1}];  score every view against covered_k.
-// Block 0 also materialises covered_k for the next launch.  score_only_cover: last launch, no scoring.
-__global__ void __launch_bounds__(256) greedy_iter_kernel(const uint64_t* rows, uint32_t words64, const uint32_t* view_ids,
-                                                          const uint32_t* row_of_id, uint32_t k, unsigned long long* best,
-                                                          const uint64_t* cov_prev, uint64_t* cov_next, int cover_only) {
-    __shared__ uint32_t s_red[8];
-    const unsigned long long prev = best[k - 1];
-    if (k > 1 && (prev >> 32) == 0ull) return;  // previous argmax had zero gain: selection is over
-    const uint32_t prev_id = 0xFFFFFFFFu - (uint32_t)(prev & 0xFFFFFFFFull);
-    const ulonglong2* rb = reinterpret_cast<const ulonglong2*>(rows + (size_t)row_of_id[prev_id] * words64);
-    const ulonglong2* cp = reinterpret_cast<const ulonglong2*>(cov_prev);
-    const ulonglong2* rv = reinterpret_cast<const ulonglong2*>(rows + (size_t)blockIdx.x * words64);
-    ulonglong2* cn = reinterpret_cast<ulonglong2*>(cov_next);
-    uint32_t c = 0;
-    for (uint32_t w = threadIdx.x; w < words64 / 2; w += blockDim.x) {
-        ulonglong2 cov = rb[w];
-        if (k > 1) {
-            const ulonglong2 o = cp[w];
-            cov.x |= o.x;
-            cov.y |= o.y;
-        }
-        if (blockIdx.x == 0) cn[w] = cov;
-        if (!cover_only) {
-            const ulonglong2 v = rv[w];
-            c += __popcll(v.x & ~cov.x) + __popcll(v.y & ~cov.y);
-        }
-    }
-    if (cover_only) return;
-    const uint32_t t = block_reduce_sum(c, s_red);
-    if (threadIdx.x == 0) atomicMax(best + k, ((unsigned long long)t << 32) | (unsigned long long)(0xFFFFFFFFu - view_ids[blockIdx.x]));
-}
-
-// Whole greedy loop in ONE persistent kernel (cooperative launch: every block is resident).  Each block keeps the
-// covered mask in shared memory and scores its rows (row r -> block r mod gridDim) against it; the per-iteration argmax
-// is one 64-bit atomicMax per block followed by a grid barrier (cooperative_groups grid sync); every block
-// then ORs the winner's row into its own copy of the mask.  Same selection rule and results as greedy_iter_kernel.
-__global__ void __launch_bounds__(256) greedy_persistent_kernel(const uint64_t* __restrict__ rows, uint32_t words64, uint32_t nrows,
-                                                                const uint32_t* __restrict__ view_ids, const uint32_t* __restrict__ row_of_id,
-                                                                uint32_t first_row, uint32_t first_id, uint32_t max_iter, unsigned long long* best,
-                                                                uint64_t* cov_out, unsigned int* arrive, int rows_in_smem) {
-    extern __shared__ uint64_t s_cov[];
-    __shared__ uint32_t s_red[8];
-    __shared__ unsigned long long s_best;
-    const uint32_t half = words64 / 2;
-    ulonglong2* cov2 = reinterpret_cast<ulonglong2*>(s_cov);
-    {
-        const ulonglong2* r0 = reinterpret_cast<const ulonglong2*>(rows + (size_t)first_row * words64);
-        uint32_t c = 0;
-        for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) {
-            const ulonglong2 v = r0[w];
-            cov2[w] = v;
-            c += __popcll(v.x) + __popcll(v.y);
-        }
-        const uint32_t t = block_reduce_sum(c, s_red);
-        if (blockIdx.x == 0 && threadIdx.x == 0) best[0] = ((unsigned long long)t << 32) | (unsigned long long)(0xFFFFFFFFu - first_id);
-        __syncthreads();
-    }
-    // the block's own rows live in shared memory after the mask (the grid barrier's __threadfence invalidates L1 every
-    // iteration, so rows left in global memory would be re-fetched from L2 each time)
-    ulonglong2* srows = cov2 + half;
-    if (rows_in_smem) {
-        uint32_t slot = 0;
-        for (uint32_t r = blockIdx.x; r < nrows; r += gridDim.x, slot++) {
-            const ulonglong2* rv = reinterpret_cast<const ulonglong2*>(rows + (size_t)r * words64);
-            for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) srows[(size_t)slot * half + w] = rv[w];
-        }
-        __syncthreads();
-    }
-    for (uint32_t k = 1; k <= max_iter; k++) {
-        unsigned long long local = 0ull;
-        uint32_t slot = 0;
-        for (uint32_t r = blockIdx.x; r < nrows; r += gridDim.x, slot++) {
-            const ulonglong2* rv = rows_in_smem ? srows + (size_t)slot * half : reinterpret_cast<const ulonglong2*>(rows + (size_t)r * words64);
-            uint32_t c = 0;
-            for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) {
-                const ulonglong2 v = rv[w];
-                const ulonglong2 cv = cov2[w];
-                c += __popcll(v.x & ~cv.x) + __popcll(v.y & ~cv.y);
-            }
-            const uint32_t t = block_reduce_sum(c, s_red);
-            if (threadIdx.x == 0) {
-                const unsigned long long packed = ((unsigned long long)t << 32) | (unsigned long long)(0xFFFFFFFFu - view_ids[r]);
-                local = packed > local ? packed : local;
-            }
-            __syncthreads();  // s_red reuse
-        }
-        // argmax across blocks + grid barrier
-        // argmax across blocks: one 64-bit atomicMax per block, then the cooperative-groups grid barrier (measured 3-7 %
-        // faster than a hand-written arrival counter with __threadfence + polling)
-        if (threadIdx.x == 0) atomicMax(best + k, local);
-        cooperative_groups::this_grid().sync();
-        if (threadIdx.x == 0) s_best = *reinterpret_cast<volatile unsigned long long*>(best + k);
-        __syncthreads();
-        const unsigned long long b = s_best;
-        if ((b >> 32) == 0ull) break;  // nothing left to gain: selection is over
-        const uint32_t rb = row_of_id[0xFFFFFFFFu - (uint32_t)(b & 0xFFFFFFFFull)];
-        const ulonglong2* rw = reinterpret_cast<const ulonglong2*>(rows + (size_t)rb * words64);
-        for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) {
-            const ulonglong2 v = rw[w];
-            ulonglong2 cv = cov2[w];
-            cv.x |= v.x;
-            cv.y |= v.y;
-            cov2[w] = cv;
-        }
-        __syncthreads();
-    }
-    if (blockIdx.x == 0) {
-        __syncthreads();
-        for (uint32_t w = threadIdx.x; w < words64; w += blockDim.x) cov_out[w] = s_cov[w];
-    }
-}
-
-// Greedy loop inside ONE thread-block cluster: the whole coverage table lives in the distributed shared memory of the
-// cluster's CTAs (row r -> CTA r mod C, slot r div C), every CTA keeps its own copy of the covered mask.  One iteration =
-// score own rows from shared memory, post the CTA's best to CTA 0 through DSMEM, ONE hardware cluster barrier, every CTA
-// reduces the C candidates itself and ORs the winner's row (read through DSMEM from its owner) into its mask.  No global
-// atomics, no polling; candidates are double-buffered so one barrier per iteration suffices.
-__global__ void __launch_bounds__(512) greedy_cluster_kernel(const uint64_t* __restrict__ rows, uint32_t words64, uint32_t nrows,
-                                                             const uint32_t* __restrict__ view_ids, const uint32_t* __restrict__ row_of_id,
-                                                             uint32_t first_row, uint32_t first_id, uint32_t max_iter, uint32_t rows_per_cta,
-                                                             unsigned long long* best, uint64_t* cov_out) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const uint32_t rank = cluster.block_rank(), C = cluster.num_blocks();
-    extern __shared__ uint64_t s_mem[];
-    __shared__ unsigned long long s_cand[2][16];
-    __shared__ uint32_t s_red[16];
-    __shared__ unsigned long long s_local;
-    const uint32_t half = words64 / 2;
-    ulonglong2* cov2 = reinterpret_cast<ulonglong2*>(s_mem);
-    ulonglong2* srows = cov2 + half;
-    // own rows -> shared memory; covered = row[first_row]
-    uint32_t nown = 0;
-    for (uint32_t r = rank; r < nrows; r += C, nown++) {
-        const ulonglong2* rv = reinterpret_cast<const ulonglong2*>(rows + (size_t)r * words64);
-        for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) srows[(size_t)nown * half + w] = rv[w];
-    }
-    {
-        const ulonglong2* r0 = reinterpret_cast<const ulonglong2*>(rows + (size_t)first_row * words64);
-        uint32_t c = 0;
-        for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) {
-            const ulonglong2 v = r0[w];
-            cov2[w] = v;
-            c += __popcll(v.x) + __popcll(v.y);
-        }
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, o);
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = c;
-        __syncthreads();
-        if (rank == 0 && threadIdx.x == 0) {
-            uint32_t t = 0;
-            for (uint32_t w = 0; w < (blockDim.x >> 5); w++) t += s_red[w];
-            best[0] = ((unsigned long long)t << 32) | (unsigned long long)(0xFFFFFFFFu - first_id);
-        }
-    }
-    cluster.sync();  // every CTA's rows are resident before anybody reads them remotely
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-    for (uint32_t k = 1; k <= max_iter; k++) {
-        // score own rows: one warp per row
-        if (threadIdx.x == 0) s_local = 0ull;
-        __syncthreads();
-        for (uint32_t slot = warp; slot < nown; slot += nwarp) {
-            const ulonglong2* rv = srows + (size_t)slot * half;
-            uint32_t c = 0;
-            for (uint32_t w = lane; w < half; w += 32) {
-                const ulonglong2 v = rv[w];
-                const ulonglong2 cv = cov2[w];
-                c += __popcll(v.x & ~cv.x) + __popcll(v.y & ~cv.y);
-            }
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(0xFFFFFFFFu, c, o);
-            if (lane == 0) atomicMax(&s_local, ((unsigned long long)c << 32) | (unsigned long long)(0xFFFFFFFFu - view_ids[rank + slot * C]));
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) *cluster.map_shared_rank(&s_cand[k & 1][rank], 0) = s_local;
-        cluster.sync();
-        // every CTA reduces the candidates posted at CTA 0
-        unsigned long long b = 0ull;
-        {
-            const unsigned long long* cand0 = cluster.map_shared_rank(&s_cand[k & 1][0], 0);
-            for (uint32_t c = 0; c < C; c++) {
-                const unsigned long long v = cand0[c];
-                b = v > b ? v : b;
-            }
-        }
-        if (rank == 0 && threadIdx.x == 0) best[k] = b;
-        if ((b >> 32) == 0ull) break;  // uniform across the cluster
-        const uint32_t rb = row_of_id[0xFFFFFFFFu - (uint32_t)(b & 0xFFFFFFFFull)];
-        const ulonglong2* rw = cluster.map_shared_rank(srows + (size_t)(rb / C) * half, rb % C);
-        for (uint32_t w = threadIdx.x; w < half; w += blockDim.x) {
-            const ulonglong2 v = rw[w];
-            ulonglong2 cv = cov2[w];
-            cv.x |= v.x;
-            cv.y |= v.y;
-            cov2[w] = cv;
-        }
-        __syncthreads();
-    }
-    cluster.sync();  // nobody exits while its shared memory may still be read remotely
-    if (rank == 0)
-        for (uint32_t w = threadIdx.x; w < words64; w += blockDim.x) cov_out[w] = s_mem[w];
-}
-
-// ensemble-uncertainty scoring (nbv_loop cases 2/3, main.cpp:2039-2161) ------------------------------------------
-// Stage 1: one thread per (view, pixel) computes the pixel's contribution(s) in the reference's double arithmetic.
-// Stage 2: one thread per view adds them in the reference's order (row-major pixels, channel order), so the score is
-// the same sequence of double additions.  NaN marks "no term" (method 2 skips variances <= 1e-10).
-__global__ void __launch_bounds__(256) ensemble_terms_kernel(const uint8_t* __restrict__ images, uint32_t E, uint32_t npix, int method,
-                                                             const double* __restrict__ log_lut, double* __restrict__ terms) {
-    const uint32_t view = blockIdx.y;
-    const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= npix) return;
-    const uchar4* base = reinterpret_cast<const uchar4*>(images) + (size_t)view * E * npix + pix;
-    double mean[3] = {0.0, 0.0, 0.0};
-    double mean_density = 0.0;
-    for (uint32_t e = 0; e < E; e++) {
-        const uchar4 px = base[(size_t)e * npix];
-        mean[0] = prvk::dadd(mean[0], (double)px.x);
-        mean[1] = prvk::dadd(mean[1], (double)px.y);
-        mean[2] = prvk::dadd(mean[2], (double)px.z);
-        mean_density = prvk::dadd(mean_density, prvk::ddiv((double)px.w, 255.0));
-    }
-    for (int c = 0; c < 3; c++) mean[c] = prvk::ddiv(mean[c], (double)E);
-    mean_density = prvk::ddiv(mean_density, (double)E);
-    double variance[3] = {0.0, 0.0, 0.0};
-    for (uint32_t e = 0; e < E; e++) {
-        const uchar4 px = base[(size_t)e * npix];
-        const double v[3] = {(double)px.x, (double)px.y, (double)px.z};
-        for (int c = 0; c < 3; c++) {
-            const double d = prvk::dsub(v[c], mean[c]);
-            variance[c] = prvk::dadd(variance[c], prvk::dmul(d, d));
-        }
-    }
-    for (int c = 0; c < 3; c++) variance[c] = prvk::ddiv(variance[c], (double)E);
-    double* out = terms + ((size_t)view * npix + pix) * 3;
-    const double nan = __longlong_as_double(0x7FF8000000000000ll);
-    if (method == 2) {
-        for (int c = 0; c < 3; c++) {
-            double t = nan;
-            if (variance[c] > 1e-10) {
-                if (log_lut) {  // E == 2: variance = (|a-b|/2)^2 exactly; host libm values
-                    const uchar4 p0 = base[0], p1 = base[npix];
-                    const int a = c == 0 ? p0.x : (c == 1 ? p0.y : p0.z), b = c == 0 ? p1.x : (c == 1 ? p1.y : p1.z);
-                    t = log_lut[a > b ? a - b : b - a];
-                } else {
-                    t = log(variance[c]);
-                }
-            }
-            out[c] = t;
-        }
-    } else {
-        out[0] = prvk::ddiv(prvk::dadd(prvk::dadd(variance[0], variance[1]), variance[2]), 3.0);
-        const double q = prvk::dsub(1.0, mean_density);
-        out[1] = prvk::dmul(q, q);
-        out[2] = nan;
-    }
-}
-
-__global__ void __launch_bounds__(32) ensemble_sum_kernel(const double* __restrict__ terms, uint32_t V, uint32_t npix, double* __restrict__ scores) {
-    const uint32_t view = blockIdx.x * blockDim.x + threadIdx.x;
-    if (view >= V) return;
-    const double* t = terms + (size_t)view * npix * 3;
-    double acc = 0.0;
-    for (size_t i = 0; i < (size_t)npix * 3; i++) {
-        const double v = t[i];
-        if (v == v) acc = prvk::dadd(acc, v);
-    }
-    scores[view] = acc;
-}
-
-// splat z-buffer -------------------------------------------------------------------------------------
-// Stage 1: one 64-bit atomicMin per point on the CORNER cell of its footprint; stage 2 takes the min over the
-// point_size x point_size corner cells that cover a pixel.  min is associative, so this equals point_size^2 atomics
-// per point on the pixels themselves.
-__global__ void __launch_bounds__(256) splat_points_kernel(const float* xyz, uint64_t P, DevCam cam, const ViewConst* views,
-                                                           uint32_t view_base, float focal, int point_size, unsigned long long* corner,
-                                                           int Wc, int Hc) {
-    const uint32_t view_local = blockIdx.y;
-    const ViewConst& vc = views[view_local + view_base];
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P) return;
-    const double x = (double)xyz[3 * i + 0], y = (double)xyz[3 * i + 1], z = (double)xyz[3 * i + 2];
-    const float xc = (float)row_apply(vc.inv + 0, x, y, z);
-    const float yc = (float)row_apply(vc.inv + 4, x, y, z);
-    const float zc = (float)row_apply(vc.inv + 8, x, y, z);
-    if (!(zc > 0.01f && zc < 1000.01f)) return;
-    const float u = fadd(fmul(fdiv(xc, zc), focal), fmul((float)cam.W, 0.5f));
-    const float v = fadd(fmul(fdiv(yc, zc), focal), fmul((float)cam.H, 0.5f));
-    if (!(u > -64.0f && u < (float)cam.W + 64.0f && v > -64.0f && v < (float)cam.H + 64.0f)) return;
-    const float off = fsub(0.5f, fmul(0.5f, (float)point_size));
-    const int lx = (int)floorf(fadd(u, off)), ly = (int)floorf(fadd(v, off));
-    const int cx = lx + point_size - 1, cy = ly + point_size - 1;
-    if (cx < 0 || cx >= Wc || cy < 0 || cy >= Hc) return;
-    const unsigned long long packed = ((unsigned long long)__float_as_uint(zc) << 32) | (unsigned long long)(uint32_t)i;
-    atomicMin(corner + ((size_t)view_local * Hc + cy) * Wc + cx, packed);
-}
-
-__global__ void __launch_bounds__(256) splat_resolve_kernel(const unsigned long long* corner, int Wc, int Hc, int W, int H, int point_size,
-                                                            const uint8_t* rgb, uint8_t* rgba, float* depth, uint32_t view_base) {
-    extern __shared__ unsigned long long s_tile[];
-    const uint32_t view_local = blockIdx.z;
-    const int tw = 32 + point_size - 1, th = 8 + point_size - 1;
-    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
-    const unsigned long long* src = corner + (size_t)view_local * Hc * Wc;
-    for (int t = threadIdx.x; t < tw * th; t += blockDim.x) {
-        const int cx = x0 + t % tw, cy = y0 + t / tw;
-        s_tile[t] = (cx < Wc && cy < Hc) ? src[(size_t)cy * Wc + cx] : ~0ull;
-    }
-    __syncthreads();
-    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    const int x = x0 + lx, y = y0 + ly;
-    if (x >= W || y >= H) return;
-    unsigned long long best = ~0ull;
-    for (int dy = 0; dy < point_size; dy++)
-        for (int dx = 0; dx < point_size; dx++) best = min(best, s_tile[(ly + dy) * tw + lx + dx]);
-    const size_t pix = ((size_t)(view_local + view_base) * H + y) * W + x;
-    uchar4 o;
-    float d = 0.0f;
-    if (best == ~0ull) {
-        o = make_uchar4(255, 255, 255, 0);
-    } else {
-        const uint32_t idx = (uint32_t)(best & 0xFFFFFFFFull);
-        o.x = rgb[3 * (size_t)idx + 0];
-        o.y = rgb[3 * (size_t)idx + 1];
-        o.z = rgb[3 * (size_t)idx + 2];
-        o.w = (o.x == 255 && o.y == 255 && o.z == 255) ? 0 : 255;  // convertToAlpha, Share_Data.hpp:771-784
-        d = __uint_as_float((uint32_t)(best >> 32));
-    }
-    reinterpret_cast<uchar4*>(rgba)[pix] = o;
-    if (depth) depth[pix] = d;
-}
+#include "kernels_common.cuh"
+#include "kernels_cast.cuh"
+#include "kernels_map.cuh"
+#include "kernels_greedy.cuh"
+#include "kernels_ensemble.cuh"
+#include "kernels_splat.cuh"
 
 // =====================================================================================================
 // context
