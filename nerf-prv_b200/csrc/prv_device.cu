@@ -76,9 +76,8 @@ struct prv_ctx {
     int occ_coarse = 0, occ_march = 0, occ_greedy = 0;
     uint32_t occ_greedy_words = 0;
     bool greedy_persistent = false;
-    // The cluster/DSMEM greedy is correct but measured slower than the grid-barrier kernel on B200 (C2 0.25 vs 0.21 ms,
-    // C3 0.43 vs 0.20 ms): it stays selectable (PRV_GREEDY_CLUSTER=1, exercised by the tests) but is not the default.
-    bool greedy_no_cluster = true;
+    // PRV_GREEDY_CLUSTER=0 forces the grid-barrier kernel (the fallback for tables larger than one cluster's shared memory)
+    bool greedy_no_cluster = false;
     int greedy_blocks_per_sm = 2;
     DevBuf d_arrive;
     DevBuf d_ens_images, d_ens_terms, d_ens_scores;
@@ -482,26 +481,32 @@ int greedy_impl(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter) {
     if ((rc = ensure(ctx, ctx->d_cov[0], 8 * (size_t)words))) return rc;
     if ((rc = ensure(ctx, ctx->d_cov[1], 8 * (size_t)words))) return rc;
     CU(cudaMemsetAsync(ctx->d_best.p, 0, 8 * ((size_t)max_iter + 2), ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_cov[0].p, 0, 8 * (size_t)words, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_cov[1].p, 0, 8 * (size_t)words, ctx->stream));
     const uint32_t* ids = ctx->gathered ? ptr<uint32_t>(ctx->d_all_ids) : ptr<uint32_t>(ctx->d_view_ids);
     const uint32_t* row_of_id = ctx->gathered ? ptr<uint32_t>(ctx->d_row_of_id_all) : ptr<uint32_t>(ctx->d_row_of_id);
     // row index of first_view in the active table
     const uint32_t first_row = h_map[first_view];
     if (first_row == kNone) return fail(ctx, PRV_ERR_INVALID, "prv_greedy: first_view %u is not a resident view id", first_view);
     const size_t cov_bytes = (size_t)words * 8;
-    // 1st choice: one thread-block cluster holding the whole table in distributed shared memory
+    // 1st choice: one thread-block cluster holding the whole table, sliced by columns, in its CTAs' shared memory
     bool launched = false;
     if (!ctx->greedy_no_cluster) {
-        for (uint32_t C = 8; C <= 16 && !launched; C *= 2) {
-            const uint32_t rpc = (ctx->g_nrows + C - 1) / C;
-            const size_t smem = cov_bytes * (1 + (size_t)rpc);
-            if (smem > (size_t)220 * 1024) continue;
+        const uint32_t T = (uint32_t)kGreedyClusterThreads;
+        for (uint32_t C = (uint32_t)kGreedyClusterMax; C >= 1 && !launched; C /= 2) {
+            const uint32_t half = words / 2;
+            const uint32_t slice = (half + C - 1) / C;
+            const uint32_t vper = (ctx->g_nrows + C - 1) / C;
+            const uint32_t vp32 = (ctx->g_nrows + 31u) & ~31u;
+            const uint32_t parts = vp32 >= T ? 1u : std::max(1u, std::min(slice, T / vp32));
+            const size_t smem = 16 * ((size_t)slice * ctx->g_nrows + slice) + 4 * (size_t)C * parts * vper;
+            if (vper > T || smem > (size_t)220 * 1024) continue;
             if (cudaFuncSetAttribute(greedy_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) break;
-            if (C > 8 && cudaFuncSetAttribute(greedy_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) break;
+            if (C > 8 && cudaFuncSetAttribute(greedy_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+                cudaGetLastError();
+                continue;
+            }
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(C);
-            cfg.blockDim = dim3(512);
+            cfg.blockDim = dim3(T);
             cfg.dynamicSmemBytes = smem;
             cfg.stream = ctx->stream;
             cudaLaunchAttribute attr[1];
@@ -517,15 +522,20 @@ int greedy_impl(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter) {
                 continue;
             }
             Span s(ctx, K_GREEDY, 1);
-            const cudaError_t e = cudaLaunchKernelEx(&cfg, greedy_cluster_kernel, ctx->g_rows, words, ctx->g_nrows, ids, row_of_id, first_row, first_view,
-                                                     max_iter, rpc, ptr<unsigned long long>(ctx->d_best), ptr<uint64_t>(ctx->d_cov[0]));
+            const cudaError_t e = cudaLaunchKernelEx(&cfg, greedy_cluster_kernel, (const uint64_t*)ctx->g_rows, words, ctx->g_nrows, ids, first_row, first_view,
+                                                     max_iter, slice, vper, parts, ptr<unsigned long long>(ctx->d_best), ptr<uint64_t>(ctx->d_cov[0]));
             if (e == cudaSuccess) {
                 launched = true;
                 ctx->greedy_persistent = true;
+                if (getenv("PRV_VERBOSE")) fprintf(stderr, "[prv] greedy: cluster of %u CTAs, slice %u x 16 B, %u views/owner, %u parts, %zu B smem\n", C, slice, vper, parts, smem);
             } else {
                 cudaGetLastError();
             }
         }
+    }
+    if (!launched) {  // (the cluster kernel writes every word of the mask itself)
+        CU(cudaMemsetAsync(ctx->d_cov[0].p, 0, 8 * (size_t)words, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_cov[1].p, 0, 8 * (size_t)words, ctx->stream));
     }
     if (launched) {
         // done
