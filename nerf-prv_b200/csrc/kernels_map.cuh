@@ -57,13 +57,41 @@ __global__ void __launch_bounds__(256) map_shell_kernel(MapBuild b) {
     }
 }
 
-// exclusive popcount prefix over the occupancy words: one block, each thread a contiguous run
-__global__ void __launch_bounds__(1024) map_prefix_kernel(MapBuild b) {
-    __shared__ uint32_t s_warp[32];
-    const unsigned long long per = (b.nwords + blockDim.x - 1) / blockDim.x;
-    const unsigned long long beg = min(b.nwords, threadIdx.x * per), end = min(b.nwords, beg + per);
+// exclusive popcount prefix over the occupancy words, two coalesced passes over kPrefixTile-word tiles:
+// map_tilesum_kernel: popcount of every tile; map_prefix_kernel: tile base = sum of the tiles before it (at most a few
+// hundred values, re-added by every block) + a block scan inside the tile.  (A single 1024-thread block with one
+// contiguous run per thread took 48 us on C2's 280k words.)
+constexpr int kPrefixThreads = 256, kPrefixPerThread = 4, kPrefixTile = kPrefixThreads * kPrefixPerThread;
+__global__ void __launch_bounds__(kPrefixThreads) map_tilesum_kernel(MapBuild b, uint32_t* tile_sums) {
+    __shared__ uint32_t s_red[8];
+    const unsigned long long w0 = (unsigned long long)blockIdx.x * kPrefixTile;
+    uint32_t c = 0;
+#pragma unroll
+    for (int j = 0; j < kPrefixPerThread; j++) {
+        const unsigned long long w = w0 + (unsigned long long)j * kPrefixThreads + threadIdx.x;
+        if (w < b.nwords) c += __popc(b.bitmap[w]);
+    }
+    const uint32_t t = block_reduce_sum(c, s_red);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(kPrefixThreads) map_prefix_kernel(MapBuild b, const uint32_t* tile_sums) {
+    __shared__ uint32_t s_red[8];
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_base;
+    uint32_t c = 0;
+    for (uint32_t i = threadIdx.x; i < blockIdx.x; i += blockDim.x) c += tile_sums[i];
+    const uint32_t base = block_reduce_sum(c, s_red);
+    if (threadIdx.x == 0) s_base = base;
+    // each thread owns kPrefixPerThread consecutive words of the tile
+    const unsigned long long w0 = (unsigned long long)blockIdx.x * kPrefixTile + (unsigned long long)threadIdx.x * kPrefixPerThread;
+    uint32_t pc[kPrefixPerThread];
     uint32_t sum = 0;
-    for (unsigned long long w = beg; w < end; w++) sum += __popc(b.bitmap[w]);
+#pragma unroll
+    for (int j = 0; j < kPrefixPerThread; j++) {
+        pc[j] = w0 + j < b.nwords ? __popc(b.bitmap[w0 + j]) : 0u;
+        sum += pc[j];
+    }
     uint32_t incl = sum;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int o = 1; o < 32; o <<= 1) {
@@ -72,19 +100,12 @@ __global__ void __launch_bounds__(1024) map_prefix_kernel(MapBuild b) {
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-        uint32_t v = s_warp[lane], iv = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, iv, o);
-            if (lane >= o) iv += t;
-        }
-        s_warp[lane] = iv - v;
-    }
-    __syncthreads();
-    uint32_t run = s_warp[warp] + incl - sum;
-    for (unsigned long long w = beg; w < end; w++) {
-        b.prefix[w] = run;
-        run += __popc(b.bitmap[w]);
+    uint32_t run = s_base + incl - sum;
+    for (int w = 0; w < warp; w++) run += s_warp[w];
+#pragma unroll
+    for (int j = 0; j < kPrefixPerThread; j++) {
+        if (w0 + j < b.nwords) b.prefix[w0 + j] = run;
+        run += pc[j];
     }
 }
 

@@ -90,7 +90,7 @@ struct prv_ctx {
     double resolution = 0;
     int lo[3] = {0, 0, 0}, n[3] = {0, 0, 0};
     DevBuf d_coarse;
-    DevBuf d_bitmap, d_bitmap_pad, d_prefix, d_leaf_of_raster, d_keys, d_rgb;
+    DevBuf d_bitmap, d_bitmap_pad, d_prefix, d_leaf_of_raster, d_keys, d_rgb, d_tilesum;
     std::vector<uint16_t> h_keys;
 
     // camera
@@ -139,6 +139,10 @@ struct prv_ctx {
     std::vector<cudaEvent_t> free_events;
     cudaEvent_t slots[16] = {};
     DevBuf d_flush;
+    // pinned staging for small device->host results and the event that marks "host inputs consumed"
+    void* h_stage = nullptr;
+    size_t h_stage_cap = 0;
+    cudaEvent_t ev_copy = nullptr;
 
     // counters (since prv_reset_counters)
     uint64_t n_launches = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -233,6 +237,42 @@ cudaError_t h2d(prv_ctx* ctx, void* dst, const void* src, size_t bytes) {
 cudaError_t d2h(prv_ctx* ctx, void* dst, const void* src, size_t bytes) {
     ctx->d2h_bytes += bytes;
     return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+}
+
+// Small results (coverage rows, counts, the greedy sequence) are copied into a ctx-owned pinned buffer and memcpy'd to
+// the caller: a device->host copy straight into pageable memory is staged by the driver piecewise and costs ~0.15 ms of
+// latency for 0.5 MB.  Pinned / registered destinations and large results are copied directly.  Synchronous.
+constexpr size_t kStageMax = (size_t)8 << 20;
+cudaError_t d2h_result(prv_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    cudaError_t e;
+    bool direct = bytes > kStageMax;
+    if (!direct) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, dst) == cudaSuccess)
+            direct = attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+        else
+            cudaGetLastError();
+    }
+    if (!direct && bytes > ctx->h_stage_cap) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr;
+        ctx->h_stage_cap = 0;
+        const size_t cap = std::max<size_t>((bytes + 4095) & ~(size_t)4095, (size_t)1 << 20);
+        if (cudaMallocHost(&ctx->h_stage, cap) == cudaSuccess)
+            ctx->h_stage_cap = cap;
+        else {
+            cudaGetLastError();
+            direct = true;
+        }
+    }
+    if (direct) {
+        if ((e = d2h(ctx, dst, src, bytes)) != cudaSuccess) return e;
+        return cudaStreamSynchronize(ctx->stream);
+    }
+    if ((e = d2h(ctx, ctx->h_stage, src, bytes)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) return e;
+    memcpy(dst, ctx->h_stage, bytes);
+    return cudaSuccess;
 }
 
 template <typename T>
@@ -345,7 +385,8 @@ int upload_views(prv_ctx* ctx, const double* pose_world, const double* init_pos,
     if ((rc = ensure(ctx, ctx->d_row_of_id, 4 * (size_t)ctx->id_space))) return rc;
     CU(h2d(ctx, ctx->d_view_ids.p, ctx->h_view_ids.data(), 4 * (size_t)V));
     CU(h2d(ctx, ctx->d_row_of_id.p, row_of_id.data(), 4 * (size_t)ctx->id_space));
-    CU(cudaStreamSynchronize(ctx->stream));  // host staging vectors go out of scope
+    // no stream sync: the three sources are pageable ctx-owned vectors, which cudaMemcpyAsync consumes (stages) before it
+    // returns, so the copies simply queue behind whatever the stream is still doing (e.g. prv_set_map's table kernels)
     ctx->V = V;
     ctx->cast_done = false;
     ctx->greedy_done = false;
@@ -660,6 +701,7 @@ int prv_create(prv_ctx** out, int device) {
         return fail(nullptr, PRV_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
     for (auto& s : ctx->slots) cudaEventCreate(&s);
+    cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
     if (const char* e = getenv("PRV_GREEDY_CLUSTER")) ctx->greedy_no_cluster = atoi(e) == 0;
     *out = ctx;
     return PRV_OK;
@@ -670,7 +712,7 @@ void prv_destroy(prv_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     prv_comm_destroy(ctx);
-    DevBuf* bufs[] = {&ctx->d_coarse, &ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
+    DevBuf* bufs[] = {&ctx->d_tilesum, &ctx->d_coarse, &ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
                       &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_tickets, &ctx->d_arrive, &ctx->d_ens_images, &ctx->d_ens_terms, &ctx->d_ens_scores, &ctx->d_row_of_id_all, &ctx->d_ing_xyz, &ctx->d_ing_rgb, &ctx->d_ing_k0,
                       &ctx->d_ing_k1, &ctx->d_ing_v0, &ctx->d_ing_v1, &ctx->d_ing_pos, &ctx->d_ing_tmp, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
                       &ctx->d_voxel_pix, &ctx->d_voxel_hit, &ctx->d_points, &ctx->d_best, &ctx->d_cov[0], &ctx->d_cov[1], &ctx->d_all_rows,
@@ -682,6 +724,8 @@ void prv_destroy(prv_ctx* ctx) {
     }
     for (auto& e : ctx->free_events) cudaEventDestroy(e);
     for (auto& s : ctx->slots) cudaEventDestroy(s);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -748,6 +792,7 @@ static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, 
     if ((rc = ensure(ctx, ctx->d_bitmap, nwords * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_prefix, nwords * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_leaf_of_raster, (size_t)N * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->d_tilesum, ((nwords + kPrefixTile - 1) / kPrefixTile + 1) * 4))) return rc;
     if (!device_ready) {
         if ((rc = ensure(ctx, ctx->d_keys, (size_t)N * 6))) return rc;
         if ((rc = ensure(ctx, ctx->d_rgb, (size_t)N * 3))) return rc;
@@ -758,6 +803,7 @@ static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, 
         else
             CU(cudaMemsetAsync(ctx->d_rgb.p, 0, (size_t)N * 3, ctx->stream));
     }
+    CU(cudaEventRecord(ctx->ev_copy, ctx->stream));  // the caller's buffers are free once this has passed
     CU(cudaMemsetAsync(ctx->d_coarse.p, 0, coarse_words * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_bitmap_pad.p, 0, pad_words * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_bitmap.p, 0, nwords * 4, ctx->stream));
@@ -779,15 +825,19 @@ static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, 
         mb.prefix = ptr<uint32_t>(ctx->d_prefix);
         mb.leaf_of_raster = ptr<uint32_t>(ctx->d_leaf_of_raster);
         mb.keys = ptr<uint16_t>(ctx->d_keys);
-        Span sp(ctx, K_OTHER, 4);
+        Span sp(ctx, K_OTHER, 5);
         map_scatter_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(mb);
         map_shell_kernel<<<(uint32_t)((pad_rows + 255) / 256), 256, 0, ctx->stream>>>(mb);
-        map_prefix_kernel<<<1, 1024, 0, ctx->stream>>>(mb);
+        const uint32_t ntiles = (uint32_t)((nwords + kPrefixTile - 1) / kPrefixTile);
+        map_tilesum_kernel<<<ntiles, kPrefixThreads, 0, ctx->stream>>>(mb, ptr<uint32_t>(ctx->d_tilesum));
+        map_prefix_kernel<<<ntiles, kPrefixThreads, 0, ctx->stream>>>(mb, ptr<uint32_t>(ctx->d_tilesum));
         map_rank_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(mb);
     }
     CU(cudaGetLastError());
-    CU(cudaStreamSynchronize(ctx->stream));
     ctx->h_keys.assign(keys, keys + (size_t)N * 3);
+    // return as soon as the host buffers have been consumed; the table kernels keep running on the ctx stream, which
+    // orders them before everything that uses the map
+    CU(cudaEventSynchronize(ctx->ev_copy));
     ctx->resolution = resolution;
     for (int a = 0; a < 3; a++) {
         ctx->lo[a] = lo[a];
@@ -1016,8 +1066,7 @@ int prv_get_bitsets(prv_ctx* ctx, uint64_t* out) {
     if (!ctx || !out) return PRV_ERR_INVALID;
     if (!ctx->cast_done) return fail(ctx, PRV_ERR_INVALID, "prv_get_bitsets: nothing cast yet");
     CU(cudaSetDevice(ctx->device));
-    CU(d2h(ctx, out, ctx->d_bitsets.p, (size_t)ctx->V * ctx->map.words64 * 8));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(d2h_result(ctx, out, ctx->d_bitsets.p, (size_t)ctx->V * ctx->map.words64 * 8));
     return PRV_OK;
 }
 
@@ -1025,8 +1074,7 @@ int prv_get_coverage_counts(prv_ctx* ctx, uint32_t* out) {
     if (!ctx || !out) return PRV_ERR_INVALID;
     if (!ctx->cast_done) return fail(ctx, PRV_ERR_INVALID, "prv_get_coverage_counts: nothing cast yet");
     CU(cudaSetDevice(ctx->device));
-    CU(d2h(ctx, out, ctx->d_counts.p, (size_t)ctx->V * 4));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(d2h_result(ctx, out, ctx->d_counts.p, (size_t)ctx->V * 4));
     return PRV_OK;
 }
 
@@ -1070,8 +1118,7 @@ int prv_get_greedy(prv_ctx* ctx, uint32_t* seq, uint32_t* gains, uint32_t* n_out
     if (!ctx->greedy_done) return fail(ctx, PRV_ERR_INVALID, "prv_get_greedy: prv_greedy_async has not run");
     CU(cudaSetDevice(ctx->device));
     std::vector<unsigned long long> best((size_t)ctx->greedy_max_iter + 2);
-    CU(d2h(ctx, best.data(), ctx->d_best.p, 8 * best.size()));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(d2h_result(ctx, best.data(), ctx->d_best.p, 8 * best.size()));
     uint32_t n = 0;
     for (uint32_t k = 0; k <= ctx->greedy_max_iter; k++) {
         const uint32_t g = (uint32_t)(best[k] >> 32);
@@ -1082,8 +1129,7 @@ int prv_get_greedy(prv_ctx* ctx, uint32_t* seq, uint32_t* gains, uint32_t* n_out
     }
     *n_out = n;
     if (covered_out) {
-        CU(d2h(ctx, covered_out, ctx->d_cov[ctx->greedy_persistent ? 0 : (n & 1)].p, 8 * (size_t)ctx->map.words64));
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU(d2h_result(ctx, covered_out, ctx->d_cov[ctx->greedy_persistent ? 0 : (n & 1)].p, 8 * (size_t)ctx->map.words64));
     }
     return PRV_OK;
 }
