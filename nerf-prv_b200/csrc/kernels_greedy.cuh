@@ -211,14 +211,18 @@ __global__ void __launch_bounds__(kGreedyClusterThreads) greedy_cluster_kernel(c
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     const uint32_t rank = cluster.block_rank(), C = cluster.num_blocks();
-    extern __shared__ ulonglong2 s_tab[];                        // [slice][nrows], then cov[slice], then s_in[C*parts][vper] (u32)
+    extern __shared__ ulonglong2 s_tab[];  // [slice][nrows], cov[slice], s_new[slice] (u128); then u32: s_in[C*parts][vper], s_pg[parts][nrows], s_nz[slice]
     __shared__ __align__(8) unsigned long long s_mbar[2];        // [0]: partial gains have arrived, [1]: candidates have arrived
     __shared__ unsigned long long s_cand[kGreedyClusterMax];     // candidates of all owners (written remotely)
     __shared__ uint32_t s_candrow[kGreedyClusterMax];
     __shared__ uint32_t s_wgain[kGreedyClusterThreads / 32], s_wnid[kGreedyClusterThreads / 32], s_wrow[kGreedyClusterThreads / 32];
     __shared__ uint32_t s_red[kGreedyClusterThreads / 32];
+    __shared__ uint32_t s_nnz[2];
     ulonglong2* cov = s_tab + (size_t)slice * nrows;
-    uint32_t* s_in = reinterpret_cast<uint32_t*>(cov + slice);
+    ulonglong2* s_new = cov + slice;                                  // newly covered bits of the non-zero words, compacted
+    uint32_t* s_in = reinterpret_cast<uint32_t*>(s_new + slice);
+    uint32_t* s_pg = s_in + (size_t)C * parts * vper;                 // running partial gain of (part, view) over this slice
+    uint32_t* s_nz = s_pg + (size_t)parts * nrows;                    // word index of each entry of s_new
     const uint32_t half = words64 / 2;
     const uint32_t w_lo = rank * slice;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
@@ -275,6 +279,22 @@ __global__ void __launch_bounds__(kGreedyClusterThreads) greedy_cluster_kernel(c
     if (threadIdx.x == 0) {
         mbar_expect_tx(mbar_in, bytes_in);
         mbar_expect_tx(mbar_cand, bytes_cand);
+        s_nnz[0] = s_nnz[1] = 0u;
+    }
+    // initial partial gains against covered = row[first_row]: the only full pass over the slice.  Afterwards
+    // gain(v) -= popcount(row(v) & newly covered), and words without newly covered bits are skipped for every view.
+    if (scorer) {
+        for (uint32_t v = v0; v < nrows; v += blockDim.x) {
+            uint32_t c = 0;
+#pragma unroll 4
+            for (uint32_t w = part; w < slice; w += parts) {
+                const ulonglong2 x = s_tab[(size_t)w * nrows + v];
+                const ulonglong2 cv = cov[w];
+                c += __popcll(x.x & ~cv.x) + __popcll(x.y & ~cv.y);
+            }
+            s_pg[(size_t)part * nrows + v] = c;
+            if (parts > 1) break;
+        }
     }
     cluster.sync();  // every CTA's mbarriers and shared memory are initialised before anybody writes into them remotely
     for (uint32_t k = 1; k <= max_iter; k++) {
@@ -282,14 +302,15 @@ __global__ void __launch_bounds__(kGreedyClusterThreads) greedy_cluster_kernel(c
         // 1. partial gains of all views over this slice -> their owners
         if (scorer) {
             uint32_t v = v0, dst = dst0, dst_bar = dst0_bar;
+            const uint32_t nnz = s_nnz[(k - 1u) & 1u];  // words that gained covered bits in the previous iteration
             for (;;) {
-                uint32_t c = 0;
-#pragma unroll 4
-                for (uint32_t w = part; w < slice; w += parts) {
-                    const ulonglong2 x = s_tab[(size_t)w * nrows + v];
-                    const ulonglong2 cv = cov[w];
-                    c += __popcll(x.x & ~cv.x) + __popcll(x.y & ~cv.y);
+                uint32_t c = s_pg[(size_t)part * nrows + v];
+                for (uint32_t i = part; i < nnz; i += parts) {
+                    const ulonglong2 x = s_tab[(size_t)s_nz[i] * nrows + v];
+                    const ulonglong2 nw = s_new[i];
+                    c -= __popcll(x.x & nw.x) + __popcll(x.y & nw.y);  // partial sums may wrap; their total does not
                 }
+                s_pg[(size_t)part * nrows + v] = c;
                 st_async_u32(dst, c, dst_bar);
                 v += blockDim.x;
                 if (parts > 1 || v >= nrows) break;
@@ -343,12 +364,17 @@ __global__ void __launch_bounds__(kGreedyClusterThreads) greedy_cluster_kernel(c
         warp_argmax(bg, bnid, win_row);
         if (rank == 0 && threadIdx.x == 0) best[k] = ((unsigned long long)bg << 32) | bnid;
         if (bg == 0u) break;  // uniform across the cluster: nothing left to gain
+        if (threadIdx.x == 0) s_nnz[(k + 1u) & 1u] = 0u;  // the list read by this iteration's scoring; refilled next iteration
         for (uint32_t w = threadIdx.x; w < slice; w += blockDim.x) {
             const ulonglong2 x = s_tab[(size_t)w * nrows + win_row];
-            ulonglong2 cv = cov[w];
-            cv.x |= x.x;
-            cv.y |= x.y;
-            cov[w] = cv;
+            const ulonglong2 cv = cov[w];
+            const ulonglong2 nw = make_ulonglong2(x.x & ~cv.x, x.y & ~cv.y);
+            if (nw.x | nw.y) {
+                cov[w] = make_ulonglong2(cv.x | x.x, cv.y | x.y);
+                const uint32_t i = atomicAdd(&s_nnz[k & 1u], 1u);
+                s_nz[i] = w;
+                s_new[i] = nw;
+            }
         }
         // every thread has read the candidates; only now may this CTA's next partials let the owners overwrite them
         __syncthreads();

@@ -538,7 +538,7 @@ int greedy_impl(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter) {
             const uint32_t vper = (ctx->g_nrows + C - 1) / C;
             const uint32_t vp32 = (ctx->g_nrows + 31u) & ~31u;
             const uint32_t parts = vp32 >= T ? 1u : std::max(1u, std::min(slice, T / vp32));
-            const size_t smem = 16 * ((size_t)slice * ctx->g_nrows + slice) + 4 * (size_t)C * parts * vper;
+            const size_t smem = 16 * ((size_t)slice * ctx->g_nrows + 2 * (size_t)slice) + 4 * ((size_t)C * parts * vper + (size_t)parts * ctx->g_nrows + slice);
             if (vper > T || smem > (size_t)220 * 1024) continue;
             if (cudaFuncSetAttribute(greedy_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) break;
             if (C > 8 && cudaFuncSetAttribute(greedy_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
