@@ -38,6 +38,12 @@ __device__ __forceinline__ void load_view_const(ViewConst& dst, const ViewConst*
     __syncthreads();
 }
 
+// the cull / coarse kernels only need the first kViewCullWords words (float pose, origin, origin key, flags)
+__device__ __forceinline__ void load_view_prefix(ViewConst& dst, const ViewConst* src) {
+    if (threadIdx.x < kViewCullWords) reinterpret_cast<uint32_t*>(&dst)[threadIdx.x] = reinterpret_cast<const uint32_t*>(src)[threadIdx.x];
+    __syncthreads();
+}
+
 __device__ __forceinline__ void write_hit(const CastParams& p, const ViewConst& vc, uint32_t view, unsigned long long pid, const CastResult& res) {
     if (res.rank != kNone) {
         uint32_t* row = p.bitsets32 + (size_t)view * (2u * p.map.words64);
@@ -82,36 +88,37 @@ __device__ __forceinline__ void block_append(bool keep, uint32_t value, uint32_t
     __syncthreads();  // s_woff / s_base are reused by the next chunk
 }
 
-// One block per 32x32 pixel region of one view (blockIdx.x = region, blockIdx.y = view); every thread owns 4 pixels,
+// One block per kCullRegions consecutive 32x32-pixel regions of one row of one view (blockIdx = (region group, region
+// row, view)): the view constants are fetched once and the region tests of the group run side by side (one warp each),
+// so the ~1.5 us of serial latency at the start of a block (constants from L2, barrier, region test) is paid once per
+// group instead of once per region (ncu had half of all stall samples there).  In a region every thread owns 4 pixels,
 // one in each 32x8 row-tile (a warp covers an 8x4 patch per row-tile).
-// Region test: the region's rays lie inside the cone around the mean corner direction whose half-angle is the largest
-// corner angle (the pixel->direction map is projective up to the mild, host-checked lens distortion, for which the
-// corners are taken 2 pixels outside the region); if that cone misses the bounding sphere of the grown AABB, no ray
-// of the region can touch the AABB and the per-pixel tests are skipped.
+// Region test: the region's rays lie inside the pyramid spanned by the four corner rays taken 2 px outside the region
+// (the pixel->direction map is affine up to the lens distortion, whose deviation inside any region was verified on the
+// host to stay within that margin).  If all eight corners of the AABB grown by 2 voxels lie outside one side plane of the
+// pyramid, no ray of the region can touch the AABB: its pixels get "no hit" with 128-bit stores and nothing else.
+constexpr int kCullRegions = 4;
 template <bool MASKED>
-__global__ void __launch_bounds__(256) cull_kernel(const CastParams p) {
-    __shared__ ViewConst s_vc;
+__global__ void __launch_bounds__(256, 8) cull_kernel(const CastParams p) {
+    __shared__ ViewConst s_vc;  // cull prefix only
     __shared__ uint32_t s_woff[4][8];
     __shared__ uint32_t s_base;
     __shared__ uint32_t s_rays[8];
-    __shared__ int s_skip;
-    const uint32_t view = blockIdx.y + p.view_base;
-    load_view_const(s_vc, p.views + view);
+    __shared__ int s_skip[kCullRegions];
+    const uint32_t view = blockIdx.z + p.view_base;
+    load_view_prefix(s_vc, p.views + view);
     const ViewConst& vc = s_vc;
     const int regions_x = (p.GW + 31) >> 5;
-    const int region_x = blockIdx.x % regions_x, region_y = blockIdx.x / regions_x;
+    const int region_y = blockIdx.y, rx0 = blockIdx.x * kCullRegions;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool view_ok = (vc.flags & kViewInMap) && !(vc.flags & kViewInObject);
     const bool fast = (vc.flags & kViewFastOk) != 0;
 
-    if (threadIdx.x < 32) {
-        // Region test (warp 0): the region's rays lie inside the pyramid spanned by the four corner rays taken 2 px
-        // outside the region (the pixel->direction map is affine up to the lens distortion, whose deviation inside any
-        // region was verified on the host to stay within that margin).  If all eight corners of the AABB grown by
-        // 2 voxels lie outside one side plane of the pyramid, no ray of the region can touch the AABB.
-        // lane = plane (0..3) * 8 + box corner (0..7): 32 dot products, one ballot.
+    if (warp < kCullRegions) {
+        // warp r tests region rx0 + r; lane = plane (0..3) * 8 + box corner (0..7): 32 dot products, one ballot
         bool skip = false;
-        if (!MASKED && view_ok && fast && p.cam.region_cull_ok) {
+        const int region_x = rx0 + warp;
+        if (!MASKED && region_x < regions_x && view_ok && fast && p.cam.region_cull_ok) {
             const int plane = lane >> 3, corner = lane & 7;
             // pyramid corners counter-clockwise in pixel space: (x0,y0) (x1,y0) (x1,y1) (x0,y1)
             const float x0 = (float)((region_x << 5) - 2), x1 = (float)((region_x << 5) + 33);
@@ -135,88 +142,100 @@ __global__ void __launch_bounds__(256) cull_kernel(const CastParams p) {
             const uint32_t bal = __ballot_sync(0xFFFFFFFFu, outside);
             skip = ((bal & 0xFFu) == 0xFFu) || ((bal & 0xFF00u) == 0xFF00u) || ((bal & 0xFF0000u) == 0xFF0000u) || ((bal & 0xFF000000u) == 0xFF000000u);
         }
-        if (lane == 0) s_skip = skip ? 1 : 0;
+        if (lane == 0) s_skip[warp] = skip ? 1 : 0;
     }
     __syncthreads();
-    if (s_skip != 0) {
-        // the whole region provably misses: record "no hit" for its pixels and leave (no compaction protocol)
-        if (p.pix_hit) {
-            const int px = (region_x << 5) + ((warp & 3) << 3) + (lane & 7);
+    const bool vec_ok = ((p.GW & 3) == 0) && ((p.pix_stride & 3ull) == 0ull);
+    uint32_t skipped_rays = 0;  // thread 0: rays of the regions skipped as a whole
+    for (int r = 0; r < kCullRegions; r++) {
+        const int region_x = rx0 + r;
+        if (region_x >= regions_x) break;  // uniform
+        if (s_skip[r] != 0) {
+            // the whole region provably misses: record "no hit" for its pixels (no compaction protocol)
+            if (p.pix_hit) {
+                if (vec_ok) {  // thread -> row t/8, 4 consecutive pixels: one 128-bit store per array
+                    const int px = (region_x << 5) + ((threadIdx.x & 7) << 2), py = (region_y << 5) + (threadIdx.x >> 3);
+                    if (px < p.GW && py < p.GH) {
+                        const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
+                        *reinterpret_cast<uint4*>(p.pix_hit + o) = make_uint4(kNone, kNone, kNone, kNone);
+                        if (p.pix_depth) *reinterpret_cast<float4*>(p.pix_depth + o) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    }
+                } else {
+                    const int px = (region_x << 5) + ((warp & 3) << 3) + (lane & 7);
 #pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
-                if (px < p.GW && py < p.GH) {
-                    const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
-                    p.pix_hit[o] = kNone;
-                    if (p.pix_depth) p.pix_depth[o] = 0.0f;
+                    for (int t = 0; t < 4; t++) {
+                        const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
+                        if (px < p.GW && py < p.GH) {
+                            const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
+                            p.pix_hit[o] = kNone;
+                            if (p.pix_depth) p.pix_depth[o] = 0.0f;
+                        }
+                    }
                 }
             }
+            skipped_rays += (uint32_t)(min(32, p.GW - (region_x << 5)) * min(32, p.GH - (region_y << 5)));
+            continue;
         }
+        uint32_t keep_mask = 0;  // bit t: this thread's pixel in row-tile t survives
+        uint32_t pids[4];
+        uint32_t nrays = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const int px = (region_x << 5) + ((warp & 3) << 3) + (lane & 7);
+            const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
+            const bool in_grid = px < p.GW && py < p.GH;
+            const unsigned long long pid = (unsigned long long)py * p.GW + px;
+            pids[t] = ((uint32_t)py << 16) | (uint32_t)px;  // queues carry (y,x) packed: no division downstream
+            bool active = in_grid && view_ok;
+            if (MASKED && active) {
+                const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
+                active = (w >> (pid & 31)) & 1u;
+            }
+            bool survive = false;
+            if (active) {
+                if (!fast) {
+                    survive = true;  // this view needs the literal march (max-range test): no cull
+                } else {
+                    float dx, dy, dz;
+                    ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
+                    survive = !loose_miss(p.map, vc, dx, dy, dz);
+                }
+            }
+            if (in_grid && !survive && p.pix_hit && (!MASKED || active)) {
+                p.pix_hit[(size_t)view * p.pix_stride + pid] = kNone;
+                if (p.pix_depth) p.pix_depth[(size_t)view * p.pix_stride + pid] = 0.0f;
+            }
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, survive);
+            nrays += __popc(__ballot_sync(0xFFFFFFFFu, active));
+            if (survive) keep_mask |= 1u << t;
+            if (lane == 0) s_woff[t][warp] = __popc(bal);
+            // lane-local rank within the warp for this row-tile, kept in the high bits
+            keep_mask |= (uint32_t)__popc(bal & ((1u << lane) - 1u)) << (8 + 6 * t);
+        }
+        if (lane == 0) s_rays[warp] = nrays;
+        __syncthreads();
         if (threadIdx.x == 0) {
-            const int w = min(32, p.GW - (region_x << 5)), h = min(32, p.GH - (region_y << 5));
-            atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)(w * h));
+            uint32_t tot = 0, rays = 0;
+            for (int t = 0; t < 4; t++)
+                for (int w = 0; w < 8; w++) {
+                    const uint32_t c = s_woff[t][w];
+                    s_woff[t][w] = tot;
+                    tot += c;
+                }
+            for (int w = 0; w < 8; w++) rays += s_rays[w];
+            s_base = tot ? atomicAdd(p.qcount + view, tot) : 0u;
+            skipped_rays += rays;  // posted once per block, below
         }
-        return;
-    }
-    const bool skip = false;
-
-    uint32_t keep_mask = 0;  // bit t: this thread's pixel in row-tile t survives
-    uint32_t pids[4];
-    uint32_t nrays = 0;
+        __syncthreads();
+        if (keep_mask & 0xFu) {
+            uint32_t* q = p.queue + (size_t)view * p.queue_cap + s_base;
 #pragma unroll
-    for (int t = 0; t < 4; t++) {
-        const int px = (region_x << 5) + ((warp & 3) << 3) + (lane & 7);
-        const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
-        const bool in_grid = px < p.GW && py < p.GH;
-        const unsigned long long pid = (unsigned long long)py * p.GW + px;
-        pids[t] = ((uint32_t)py << 16) | (uint32_t)px;  // queues carry (y,x) packed: no division downstream
-        bool active = in_grid && view_ok;
-        if (MASKED && active) {
-            const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
-            active = (w >> (pid & 31)) & 1u;
+            for (int t = 0; t < 4; t++)
+                if (keep_mask & (1u << t)) q[s_woff[t][warp] + ((keep_mask >> (8 + 6 * t)) & 63u)] = pids[t];
         }
-        bool survive = false;
-        if (active && !skip) {
-            if (!fast) {
-                survive = true;  // this view needs the literal march (max-range test): no cull
-            } else {
-                float dx, dy, dz;
-                ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
-                survive = !loose_miss(p.map, vc, dx, dy, dz);
-            }
-        }
-        if (in_grid && !survive && p.pix_hit && (!MASKED || active)) {
-            p.pix_hit[(size_t)view * p.pix_stride + pid] = kNone;
-            if (p.pix_depth) p.pix_depth[(size_t)view * p.pix_stride + pid] = 0.0f;
-        }
-        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, survive);
-        nrays += __popc(__ballot_sync(0xFFFFFFFFu, active));
-        if (survive) keep_mask |= 1u << t;
-        if (lane == 0) s_woff[t][warp] = __popc(bal);
-        // lane-local rank within the warp for this row-tile, kept in the high bits
-        keep_mask |= (uint32_t)__popc(bal & ((1u << lane) - 1u)) << (8 + 6 * t);
+        __syncthreads();  // s_woff / s_base / s_rays are reused by the next region
     }
-    if (lane == 0) s_rays[warp] = nrays;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0, rays = 0;
-        for (int t = 0; t < 4; t++)
-            for (int w = 0; w < 8; w++) {
-                const uint32_t c = s_woff[t][w];
-                s_woff[t][w] = tot;
-                tot += c;
-            }
-        for (int w = 0; w < 8; w++) rays += s_rays[w];
-        s_base = tot ? atomicAdd(p.qcount + view, tot) : 0u;
-        if (rays) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)rays);
-    }
-    __syncthreads();
-    if (keep_mask & 0xFu) {
-        uint32_t* q = p.queue + (size_t)view * p.queue_cap + s_base;
-#pragma unroll
-        for (int t = 0; t < 4; t++)
-            if (keep_mask & (1u << t)) q[s_woff[t][warp] + ((keep_mask >> (8 + 6 * t)) & 63u)] = pids[t];
-    }
+    if (threadIdx.x == 0 && skipped_rays) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)skipped_rays);
 }
 
 // exclusive prefix of chunk counts (chunk rays each) over the views of this launch -> s_prefix[0..nviews]
@@ -252,21 +271,30 @@ __global__ void __launch_bounds__(256) coarse_kernel(const CastParams p) {
     __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
     __shared__ uint32_t s_woff[8];
     __shared__ uint32_t s_base;
-    __shared__ uint32_t s_ticket;
+    __shared__ uint32_t s_ticket, s_vl;
+    if (threadIdx.x == 0) s_vl = 0;
     build_chunk_prefix(p.qcount + p.view_base, p.nviews, s_prefix, blockDim.x);
     const uint32_t total = s_prefix[p.nviews];
     uint32_t cur_view = 0xFFFFFFFFu;
     uint32_t vl = 0;
     for (;;) {
-        if (threadIdx.x == 0) s_ticket = atomicAdd(p.tickets + 0, 1u);
+        if (threadIdx.x == 0) {
+            const uint32_t t = atomicAdd(p.tickets + 0, 1u);
+            s_ticket = t;
+            if (t < total) {
+                uint32_t v = s_vl;
+                while (s_prefix[v + 1] <= t) v++;  // tickets grow monotonically within a block: amortised O(1)
+                s_vl = v;
+            }
+        }
         __syncthreads();
         const uint32_t g = s_ticket;
         if (g >= total) break;
-        while (s_prefix[vl + 1] <= g) vl++;  // tickets grow monotonically within a block: amortised O(1)
+        vl = s_vl;
         const uint32_t view = vl + p.view_base;
         if (view != cur_view) {
             __syncthreads();
-            load_view_const(s_vc, p.views + view);
+            load_view_prefix(s_vc, p.views + view);
             cur_view = view;
         }
         const ViewConst& vc = s_vc;

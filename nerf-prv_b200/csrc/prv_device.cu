@@ -480,7 +480,7 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
             }
             {
                 Span s(ctx, K_CULL, 2);
-                const dim3 rgrid((uint32_t)(((p.GW + 31) / 32) * ((p.GH + 31) / 32)), vn);
+                const dim3 rgrid((uint32_t)(((p.GW + 31) / 32 + kCullRegions - 1) / kCullRegions), (uint32_t)((p.GH + 31) / 32), vn);
                 if (voxel)
                     cull_kernel<true><<<rgrid, 256, 0, ctx->stream>>>(p);
                 else
