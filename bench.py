@@ -269,15 +269,19 @@ def run_own(args):
         rgb_h, _r = pinned(np.ascontiguousarray(w["map_rgb"]))
         pw_h, _p = pinned(pw)
         ip_h, _i = pinned(ip)
+        # result buffers of the step (coverage rows + counts) are caller-owned pinned memory too
+        bits_h, _b = pinned(np.zeros((pw.shape[0], ctx.words), dtype=np.uint64))
+        cnt_h, _c = pinned(np.zeros(pw.shape[0], dtype=np.uint32))
         pinned_note = "pinned"
     except Exception:
         keys_h, rgb_h, pw_h, ip_h = w["keys"], w["map_rgb"], pw, ip
+        bits_h = cnt_h = None
         pinned_note = "pageable"
     def e2e_step():
         ctx.set_map(keys_h, rgb_h, w["resolution"])
         ctx.set_camera(w["intr"], 1.0)
         if not strong:
-            ctx.cast_views(pw_h, ip_h, mode=prv.MODE_DENSE, want_bitsets=True, want_counts=True)
+            ctx.cast_views(pw_h, ip_h, mode=prv.MODE_DENSE, want_bitsets=True, want_counts=True, out_bitsets=bits_h, out_counts=cnt_h)
         else:
             ctx.set_views(pw_h, ip_h, view_ids=ids)
             ctx.cast_async(prv.MODE_DENSE, False)

@@ -375,13 +375,24 @@ class Context:
         return st.as_dict()
 
     # host-buffer one-call API
-    def cast_views(self, pose_world, init_pos, mode=MODE_DENSE, want_bitsets=True, want_counts=True, want_hit_rank=False, want_depth=False):
+    def cast_views(self, pose_world, init_pos, mode=MODE_DENSE, want_bitsets=True, want_counts=True, want_hit_rank=False, want_depth=False,
+                   out_bitsets=None, out_counts=None):
+        """prv_cast_views.  out_bitsets / out_counts: caller-owned result buffers ([V][words] uint64, [V] uint32), e.g. pinned
+        host memory, which the library then fills with a direct device->host copy."""
         pw = np.ascontiguousarray(np.asarray(pose_world, dtype=np.float64).reshape(-1, 16))
         ip = np.ascontiguousarray(np.asarray(init_pos, dtype=np.float64).reshape(-1, 3))
         V = pw.shape[0]
         words = self.words
-        bits = np.zeros((V, words), dtype=np.uint64) if want_bitsets else None
-        counts = np.zeros(V, dtype=np.uint32) if want_counts else None
+        bits = None
+        if want_bitsets:
+            bits = out_bitsets if out_bitsets is not None else np.empty((V, words), dtype=np.uint64)
+            if bits.shape != (V, words) or bits.dtype != np.uint64 or not bits.flags.c_contiguous:
+                raise ValueError("out_bitsets must be a C-contiguous uint64 array of shape (%d, %d)" % (V, words))
+        counts = None
+        if want_counts:
+            counts = out_counts if out_counts is not None else np.empty(V, dtype=np.uint32)
+            if counts.shape != (V,) or counts.dtype != np.uint32 or not counts.flags.c_contiguous:
+                raise ValueError("out_counts must be a C-contiguous uint32 array of shape (%d,)" % V)
         hit = None
         if want_hit_rank:
             hit = np.zeros((V, self.intr.height, self.intr.width) if mode == MODE_DENSE else (V, self.full_voxels), dtype=np.uint32)
