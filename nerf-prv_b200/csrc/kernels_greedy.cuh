@@ -319,6 +319,11 @@ __global__ void __launch_bounds__(kGreedyClusterThreads) greedy_cluster_kernel(c
                 dst_bar = map_to_cta(mbar_in, o);
             }
         }
+        // Block barrier: this iteration's reads of s_nnz / s_nz / s_new are finished before step 3 rewrites them.  (The
+        // message chain partials -> candidates already orders them, but only through other CTAs; the barrier makes the
+        // order local and visible to compute-sanitizer racecheck.  It is off the critical path: the owners below have to
+        // wait for every CTA's partials anyway.)
+        __syncthreads();
         // 2. owner: total gain of each owned view, arg-max (largest gain, then lowest view id; the row index rides along),
         //    sent to every CTA.  Only the warps that hold owner threads take part.
         if (warp < own_warps) {
