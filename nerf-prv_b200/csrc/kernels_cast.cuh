@@ -266,7 +266,7 @@ __device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint3
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256) coarse_kernel(const CastParams p) {
+__global__ void __launch_bounds__(256, 8) coarse_kernel(const CastParams p) {
     __shared__ ViewConst s_vc;
     __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
     __shared__ uint32_t s_woff[8];

@@ -32,8 +32,11 @@ __global__ void __launch_bounds__(256) map_scatter_kernel(MapBuild b) {
     for (int K = cl[2]; K <= ch[2]; K++)
         for (int J = cl[1]; J <= ch[1]; J++)
             for (int I = cl[0]; I <= ch[0]; I++) {
+                // thousands of voxels mark the same few coarse words: test first (a stale read only costs a redundant
+                // atomic), otherwise the same-address atomics serialise in L2 and dominate the kernel
                 const uint32_t c = (uint32_t)((K * b.nc[1] + J) * b.nc[0] + I);
-                atomicOr(b.coarse + (c >> 5), 1u << (c & 31));
+                const uint32_t bit = 1u << (c & 31);
+                if (!(__ldcg(b.coarse + (c >> 5)) & bit)) atomicOr(b.coarse + (c >> 5), bit);
             }
 }
 
