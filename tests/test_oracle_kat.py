@@ -2,6 +2,8 @@
 
 Analytic castRay scenes, key maths, projection quirks, leaf order, frozen greedy and splat definitions.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -230,3 +232,15 @@ def test_reference_thread_structure_equals_plain_precept(prv, orc, synth):
     ok, a, ra = m.precept(it, w["pose_world"][1], w["init_pos"][1])
     ok2, b, rb = m.precept_threads(it, w["pose_world"][1], w["init_pos"][1], num_of_thread=20)
     assert ok and ok2 and np.array_equal(ra, rb) and np.array_equal(a, b) and (ra != orc.NONE).sum() > 50
+
+
+def test_exact_skip_ahead_of_the_tmax_recurrence_matches_the_literal_loop(tmp_path):
+    """tests/cpp/test_advance.cpp: the binade-wise exact skip-ahead of `t = fl(t + d)` (a measured dead end, DESIGN.md
+    section 7) reproduces `for k < n: t = t + d` bit for bit, ties included."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "test_advance"
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-o", str(exe), os.path.join(root, "tests", "cpp", "test_advance.cpp")], check=True)
+    r = subprocess.run([str(exe), "2000000"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout[-2000:]
