@@ -244,3 +244,105 @@ def test_exact_skip_ahead_of_the_tmax_recurrence_matches_the_literal_loop(tmp_pa
     subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-o", str(exe), os.path.join(root, "tests", "cpp", "test_advance.cpp")], check=True)
     r = subprocess.run([str(exe), "2000000"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout[-2000:]
+
+
+def _py_cast_ray(occ, origin, dirp, res, max_range, ignore_unknown=True):
+    """castRay of OctoMap 1.9.x written a second time, independently of oracle/prv_oracle.cpp, straight from the frozen
+    spec in SURVEY.md section 8(c), with numpy scalars standing in for the C types (np.float32 = float, python float =
+    double).  Slow: small scenes only.  Returns (found, key or None, steps)."""
+    f32 = np.float32
+    rf = 1.0 / res
+    key = []
+    for i in range(3):
+        k = int(np.floor(rf * float(origin[i]))) + 32768
+        if k < 0 or k >= 65536:
+            return False, None, 0
+        key.append(k)
+    if tuple(key) in occ:
+        return True, tuple(key), 0
+    if not ignore_unknown:
+        return False, None, 0
+    d = [f32(dirp[0]), f32(dirp[1]), f32(dirp[2])]
+    nsq = f32(f32(f32(d[0] * d[0]) + f32(d[1] * d[1])) + f32(d[2] * d[2]))
+    ln = float(np.sqrt(np.float64(nsq)))
+    if ln > 0:
+        d = [f32(x / f32(ln)) for x in d]
+    step, tmax, tdelta = [0] * 3, [0.0] * 3, [0.0] * 3
+    big = float(np.finfo(np.float64).max)
+    for i in range(3):
+        step[i] = 1 if d[i] > 0 else (-1 if d[i] < 0 else 0)
+        if step[i] != 0:
+            border = (float(key[i] - 32768) + 0.5) * res
+            border += float(step[i] * res * 0.5)
+            tmax[i] = (border - float(origin[i])) / float(d[i])
+            tdelta[i] = res / abs(float(d[i]))
+        else:
+            tmax[i] = tdelta[i] = big
+    if step == [0, 0, 0]:
+        return False, None, 0
+    steps = 0
+    while True:
+        if tmax[0] < tmax[1]:
+            dim = 0 if tmax[0] < tmax[2] else 2
+        else:
+            dim = 1 if tmax[1] < tmax[2] else 2
+        if (step[dim] < 0 and key[dim] == 0) or (step[dim] > 0 and key[dim] == 65535):
+            return False, None, steps
+        key[dim] += step[dim]
+        tmax[dim] += tdelta[dim]
+        steps += 1
+        if max_range > 0:
+            d2 = 0.0
+            for j in range(3):
+                end = f32((float(key[j] - 32768) + 0.5) * res)
+                df = f32(end - f32(origin[j]))
+                d2 += float(f32(df * df))
+            if d2 > max_range * max_range:
+                return False, None, steps
+        if tuple(key) in occ:
+            return True, tuple(key), steps
+        if not ignore_unknown:
+            return False, None, steps
+
+
+@pytest.mark.parametrize("res,seed", [(0.002, 1), (0.001, 2), (0.0025, 3)])
+def test_castray_agrees_with_an_independent_python_restatement(orc, res, seed):
+    """Random small scenes: the C++ oracle and a line-by-line Python restatement of the same frozen spec must return the
+    same hit voxel and the same number of DDA steps for every ray (generic directions, axis-parallel and exactly diagonal
+    ones, origins on and off voxel centres, short and unlimited max range)."""
+    rng = np.random.default_rng(seed)
+    o = 32768
+    keys = np.unique(rng.integers(o - 14, o + 15, size=(260, 3)), axis=0)
+    keys = keys[np.any(np.abs(keys - o) > 2, axis=1)]  # keep the origin neighbourhood free
+    # leaf (Morton) order is what Map.from_keys expects: sort by interleaved code, z most significant within a triple
+    def morton(k):
+        c = 0
+        for b in range(16):
+            c |= ((int(k[0]) >> b) & 1) << (3 * b) | ((int(k[1]) >> b) & 1) << (3 * b + 1) | ((int(k[2]) >> b) & 1) << (3 * b + 2)
+        return c
+    keys = np.array(sorted(keys.tolist(), key=morton), dtype=np.uint16)
+    m = orc.Map.from_keys(keys, np.full((len(keys), 3), 7, dtype=np.uint8), res)
+    occ = {tuple(int(x) for x in k) for k in keys}
+    n_hit = 0
+    for i in range(160):
+        origin = np.array([(rng.integers(-2, 3) + (0.5 if i % 3 else rng.random())) * res for _ in range(3)], dtype=np.float32)
+        kind = i % 8
+        if kind == 0:
+            d = np.zeros(3, dtype=np.float32); d[rng.integers(0, 3)] = rng.choice([-1.0, 1.0])
+        elif kind == 1:
+            d = rng.choice([-1.0, 1.0], size=3).astype(np.float32)                      # exact diagonal: ties at every step
+        elif kind == 2:
+            d = np.array([rng.choice([-2.0, 2.0]), rng.choice([-1.0, 1.0]), 0.0], dtype=np.float32)
+        else:
+            d = rng.normal(size=3).astype(np.float32)
+        max_range = [1.0, 0.02, 0.0, 0.011][i % 4]
+        st = orc.CastStats()
+        found, end, rank = m.cast_ray(origin, d, True, max_range, st)
+        p_found, p_key, p_steps = _py_cast_ray(occ, origin, d, res, max_range)
+        assert found == p_found, (i, origin, d, max_range)
+        assert st.steps == p_steps, (i, st.steps, p_steps)
+        if found:
+            n_hit += 1
+            assert tuple(int(x) for x in keys[rank]) == p_key
+            assert end.tolist() == [np.float32((p_key[j] - 32768 + 0.5) * res) for j in range(3)]
+    assert n_hit > 10
