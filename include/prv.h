@@ -12,7 +12,13 @@
  *   - extern "C", POD only, caller owns every host buffer, ctx owns device memory / stream / events.
  *   - every function returns PRV_OK (0) or a negative prv_status; nothing throws or aborts across the
  *     ABI; prv_last_error(ctx) returns a static/ctx-owned message for the last failure.
- *   - calls are synchronous at return unless named *_async; one ctx per GPU; a ctx is not re-entrant.
+ *   - calls are synchronous at return unless named *_async: host INPUT buffers have been consumed and host
+ *     OUTPUT buffers are filled when a call returns.  Device work that only produces device-resident state
+ *     (the lookup tables built by prv_set_map, the view table of prv_set_views) may still be running on the
+ *     ctx stream at return; every later call is ordered behind it on that stream, and a CUDA error of such
+ *     work is reported by the next call that synchronises.  One ctx per GPU; a ctx is not re-entrant.
+ *   - small results (coverage rows, counts, greedy sequence) are copied with a direct device-to-host DMA
+ *     when the caller's buffer is pinned / registered host memory, else through a ctx-owned pinned buffer.
  *   - there is NO CPU fallback: without a CUDA device prv_create fails with PRV_ERR_NO_DEVICE.
  *   - matrices are row-major double[16]; "pose_world" is the reference's view_pose_world
  *     (= now_camera_pose_world * view.pose.inverse(), main.cpp:72,109).

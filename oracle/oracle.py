@@ -1,7 +1,9 @@
 """ctypes loader for the CPU oracle (oracle/prv_oracle.cpp).
 
 TEST INFRASTRUCTURE ONLY -- may be imported from tests/, __graft_entry__.smoke() and bench.py's
-cpu_baseline / --impl reference legs, never from the product package.  PARITY UNPINNED (see prv_oracle.h).
+cpu_baseline / --impl reference legs, never from the product package.  PARITY UNPINNED for castRay and the pose maths
+(OctoMap / Eigen are not available; see prv_oracle.h); the camera functions ARE pinned against the reference's own code
+compiled into oracle/_ref/librs2_ref.so (ref_rs2 below, tests/test_oracle_kat.py).
 """
 import ctypes as C
 import os
@@ -103,6 +105,51 @@ def lib():
     L.orc_score_ensemble.restype = C.c_int
     _lib = L
     return L
+
+
+_REF_RS2_PATH = os.path.join(_HERE, "_ref", "librs2_ref.so")
+_REF_HDR = "/root/reference/PRV_simulation/Share_Data.hpp"
+_ref_rs2 = None
+
+
+def build_ref(force=False):
+    """oracle/_ref/librs2_ref.so: the reference's own rs2_project_point_to_pixel / rs2_deproject_pixel_to_point
+    (Share_Data.hpp:67-196) compiled from where they lie (oracle/Makefile target `ref`).  Needs /root/reference; returns the
+    path, or None when neither the reference nor a previously built library is there."""
+    if os.path.exists(_REF_HDR) and (force or not os.path.exists(_REF_RS2_PATH)):
+        subprocess.run(["make", "-C", _HERE, "-B", "ref"], check=True, stdout=subprocess.DEVNULL)
+    return _REF_RS2_PATH if os.path.exists(_REF_RS2_PATH) else None
+
+
+def ref_rs2():
+    """ctypes handle of oracle/_ref/librs2_ref.so (the real reference camera code), or None if it is not available."""
+    global _ref_rs2
+    if _ref_rs2 is None:
+        path = build_ref()
+        if path is None:
+            return None
+        L = C.CDLL(path)
+        f = C.c_float
+        L.ref_rs2_project_point_to_pixel.argtypes = [C.POINTER(f), C.POINTER(Intrinsics), C.POINTER(f)]
+        L.ref_rs2_deproject_pixel_to_point.argtypes = [C.POINTER(f), C.POINTER(Intrinsics), C.POINTER(f), f]
+        L.ref_rs2_sizeof_intrinsics.restype = C.c_int
+        assert L.ref_rs2_sizeof_intrinsics() == C.sizeof(Intrinsics)
+        _ref_rs2 = L
+    return _ref_rs2
+
+
+def ref_project_point_to_pixel(intr, point):
+    p = np.ascontiguousarray(point, dtype=np.float32)
+    out = np.zeros(2, dtype=np.float32)
+    ref_rs2().ref_rs2_project_point_to_pixel(_ptr(out, C.c_float), C.byref(intr), _ptr(p, C.c_float))
+    return out
+
+
+def ref_deproject_pixel_to_point(intr, pixel, depth):
+    p = np.ascontiguousarray(pixel, dtype=np.float32)
+    out = np.zeros(3, dtype=np.float32)
+    ref_rs2().ref_rs2_deproject_pixel_to_point(_ptr(out, C.c_float), C.byref(intr), _ptr(p, C.c_float), C.c_float(depth))
+    return out
 
 
 def make_intrinsics(width, height, fx, fy, ppx, ppy, model=2, coeffs=(0, 0, 0, 0, 0)):

@@ -1,5 +1,5 @@
 /*
- * prv_oracle.cpp -- CPU ORACLE (test infrastructure only; see prv_oracle.h).  PARITY UNPINNED.
+ * prv_oracle.cpp -- CPU ORACLE (test infrastructure only; see prv_oracle.h).  Camera maths pinned to the reference's compiled code; castRay / pose maths PARITY UNPINNED.
  *
  * Build: g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC  (see oracle/Makefile).  -ffp-contract=off
  * is REQUIRED: every float/double expression below must round exactly as written (no FMA).
@@ -232,17 +232,19 @@ void project_point_to_pixel(float pixel[2], const orc_intrinsics* in, const floa
         x = dx;
         y = dy;
     }
+    // models 3 / 5: the reference is C++ with `using namespace std` (Share_Data.hpp:63), so tan / atan on float arguments
+    // are the FLOAT overloads of <cmath>; checked against the reference's compiled code (oracle/_ref, tests/test_oracle_kat.py)
     if (in->model == 3) {
         float r = sqrtf(x * x + y * y);
         if (r < FLT_EPSILON) r = FLT_EPSILON;
-        float rd = (float)(1.0f / in->coeffs[0] * atan(2 * r * tan(in->coeffs[0] / 2.0f)));
+        float rd = (float)(1.0f / in->coeffs[0] * std::atan(2 * r * std::tan(in->coeffs[0] / 2.0f)));
         x *= rd / r;
         y *= rd / r;
     }
     if (in->model == 5) {
         float r = sqrtf(x * x + y * y);
         if (r < FLT_EPSILON) r = FLT_EPSILON;
-        float theta = atan(r);
+        float theta = std::atan(r);
         float theta2 = theta * theta;
         float series = 1 + theta2 * (in->coeffs[0] + theta2 * (in->coeffs[1] + theta2 * (in->coeffs[2] + theta2 * in->coeffs[3])));
         float rd = theta * series;
@@ -277,14 +279,14 @@ void deproject_pixel_to_point(float point[3], const orc_intrinsics* in, const fl
             theta -= f / df;
             theta2 = theta * theta;
         }
-        float r = tan(theta);
+        float r = std::tan(theta);
         x *= r / rd;
         y *= r / rd;
     }
     if (in->model == 3) {
         float rd = sqrtf(x * x + y * y);
         if (rd < FLT_EPSILON) rd = FLT_EPSILON;
-        float r = (float)(tan(in->coeffs[0] * rd) / atan(2 * tan(in->coeffs[0] / 2.0f)));
+        float r = (float)(std::tan(in->coeffs[0] * rd) / std::atan(2 * std::tan(in->coeffs[0] / 2.0f)));
         x *= r / rd;
         y *= r / rd;
     }

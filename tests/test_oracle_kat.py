@@ -346,3 +346,31 @@ def test_castray_agrees_with_an_independent_python_restatement(orc, res, seed):
             assert tuple(int(x) for x in keys[rank]) == p_key
             assert end.tolist() == [np.float32((p_key[j] - 32768 + 0.5) * res) for j in range(3)]
     assert n_hit > 10
+
+
+@pytest.mark.parametrize("model", [0, 1, 2, 3, 4, 5])
+def test_camera_maths_pinned_against_the_reference_code(orc, model):
+    """oracle/_ref/librs2_ref.so is the reference's OWN rs2_project_point_to_pixel / rs2_deproject_pixel_to_point
+    (Share_Data.hpp:92-196) compiled from /root/reference by `make -C oracle ref`; the oracle's restatement must agree
+    with it bit for bit -- D435 intrinsics of DefaultConfiguration.yaml:38-49 and stronger distortion, every model."""
+    if orc.ref_rs2() is None:
+        pytest.skip("oracle/_ref/librs2_ref.so not built and /root/reference not present")
+    rng = np.random.default_rng(100 + model)
+    yaml_coeffs = (0.12042199820280075, -0.21373499929904938, -0.0021210000850260258, 0.0053860000334680080, 0.0)
+    strong = (0.31, -0.47, 0.013, -0.009, 0.12)
+    n_cmp = 0
+    for coeffs in (yaml_coeffs, strong, (0, 0, 0, 0, 0)):
+        it = orc.make_intrinsics(1280, 720, 915.60669, 913.32666, 647.14532, 372.51532, model, coeffs)
+        for _ in range(400):
+            pt = np.array([rng.normal() * 0.2, rng.normal() * 0.2, 0.05 + rng.random()], dtype=np.float32)
+            a, b = orc.project_point_to_pixel(it, pt), orc.ref_project_point_to_pixel(it, pt)
+            assert a.tobytes() == b.tobytes(), (model, coeffs, pt, a, b)
+            if model != 1:  # the reference asserts on deprojecting a forward-distorted image
+                px = np.array([rng.random() * 1281, rng.random() * 721], dtype=np.float32)
+                if rng.random() < 0.3:
+                    px = np.floor(px)  # integer pixels: what project_pixel_to_ray_end passes (main.cpp:253)
+                depth = 1.0 if rng.random() < 0.7 else float(np.float32(rng.random() + 0.1))
+                a, b = orc.deproject_pixel_to_point(it, px, depth), orc.ref_deproject_pixel_to_point(it, px, depth)
+                assert a.tobytes() == b.tobytes(), (model, coeffs, px, depth, a, b)
+            n_cmp += 1
+    assert n_cmp == 1200
