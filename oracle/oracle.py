@@ -1,9 +1,10 @@
 """ctypes loader for the CPU oracle (oracle/prv_oracle.cpp).
 
 TEST INFRASTRUCTURE ONLY -- may be imported from tests/, __graft_entry__.smoke() and bench.py's
-cpu_baseline / --impl reference legs, never from the product package.  PARITY UNPINNED for castRay and the pose maths
-(OctoMap / Eigen are not available; see prv_oracle.h); the camera functions ARE pinned against the reference's own code
-compiled into oracle/_ref/librs2_ref.so (ref_rs2 below, tests/test_oracle_kat.py).
+cpu_baseline / --impl reference legs, never from the product package.  Camera maths, View pose logic and the per-voxel
+precept logic are pinned against the reference's own code compiled into oracle/_ref/ (ref_* below,
+tests/test_oracle_kat.py); PARITY UNPINNED for OctoMap's castRay / key maths and Eigen's rounding (libraries absent; see
+prv_oracle.h).
 """
 import ctypes as C
 import os
@@ -113,10 +114,11 @@ _ref_rs2 = None
 
 
 def build_ref(force=False):
-    """oracle/_ref/librs2_ref.so: the reference's own rs2_project_point_to_pixel / rs2_deproject_pixel_to_point
-    (Share_Data.hpp:67-196) compiled from where they lie (oracle/Makefile target `ref`).  Needs /root/reference; returns the
-    path, or None when neither the reference nor a previously built library is there."""
-    if os.path.exists(_REF_HDR) and (force or not os.path.exists(_REF_RS2_PATH)):
+    """oracle/_ref/*.so: the compilable parts of the reference (rs2_* camera functions, class View, precept_thread_process)
+    built from where they lie (oracle/Makefile target `ref`).  Needs /root/reference; returns the path of librs2_ref.so, or
+    None when neither the reference nor previously built libraries are there."""
+    have_all = all(os.path.exists(os.path.join(_HERE, "_ref", f)) for f in ("librs2_ref.so", "libview_ref.so", "libprecept_ref.so"))
+    if os.path.exists(_REF_HDR) and (force or not have_all):
         subprocess.run(["make", "-C", _HERE, "-B", "ref"], check=True, stdout=subprocess.DEVNULL)
     return _REF_RS2_PATH if os.path.exists(_REF_RS2_PATH) else None
 
@@ -136,6 +138,56 @@ def ref_rs2():
         assert L.ref_rs2_sizeof_intrinsics() == C.sizeof(Intrinsics)
         _ref_rs2 = L
     return _ref_rs2
+
+
+_REF_VIEW_PATH = os.path.join(_HERE, "_ref", "libview_ref.so")
+_ref_view = None
+
+
+def ref_view():
+    """ctypes handle of oracle/_ref/libview_ref.so: the reference's own `class View` (View_Space.hpp:40-199) compiled
+    against oracle/ref_eigen_shim.hpp, or None if it is not available."""
+    global _ref_view
+    if _ref_view is None:
+        build_ref()
+        if not os.path.exists(_REF_VIEW_PATH):
+            return None
+        L = C.CDLL(_REF_VIEW_PATH)
+        d = C.c_double
+        L.ref_view_get_next_camera_pos.argtypes = [C.POINTER(d), C.POINTER(d), C.POINTER(d), C.c_int, C.POINTER(d)]
+        _ref_view = L
+    return _ref_view
+
+
+def ref_view_pose(init_pos, object_center, now_pose=None, type_of_pose=0):
+    """View::get_next_camera_pos of the reference itself -> view.pose (4x4)."""
+    now = _d16(np.eye(4) if now_pose is None else now_pose)
+    ip = np.ascontiguousarray(init_pos, dtype=np.float64)
+    oc = np.ascontiguousarray(object_center, dtype=np.float64)
+    out = np.zeros(16)
+    ref_view().ref_view_get_next_camera_pos(_ptr(now, C.c_double), _ptr(ip, C.c_double), _ptr(oc, C.c_double), int(type_of_pose), _ptr(out, C.c_double))
+    return out.reshape(4, 4)
+
+
+_REF_PRECEPT_PATH = os.path.join(_HERE, "_ref", "libprecept_ref.so")
+_ref_precept = None
+
+
+def ref_precept_lib():
+    """ctypes handle of oracle/_ref/libprecept_ref.so: the reference's own Perception_3D::precept_thread_process
+    (main.cpp:238-284) + project_pixel_to_ray_end (Share_Data.hpp:719-726) compiled against the Eigen / OctoMap / PCL
+    shims (castRay & co. answered by this oracle), or None if it is not available."""
+    global _ref_precept
+    if _ref_precept is None:
+        build_ref()
+        if not os.path.exists(_REF_PRECEPT_PATH):
+            return None
+        lib()  # libprv_oracle.so must be loadable (the shim calls into it)
+        L = C.CDLL(_REF_PRECEPT_PATH)
+        L.ref_precept.argtypes = [C.c_void_p, C.c_double, C.POINTER(Intrinsics), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_void_p]
+        L.ref_precept.restype = C.c_int
+        _ref_precept = L
+    return _ref_precept
 
 
 def ref_project_point_to_pixel(intr, point):
@@ -292,6 +344,15 @@ class Map:
         ok = lib().orc_precept(self._h, C.byref(intr), _ptr(pw, C.c_double), _ptr(ip, C.c_double), max_range,
                                out.ctypes.data_as(C.c_void_p), _ptr(ranks, C.c_uint32), None if stats is None else C.byref(stats))
         return bool(ok), out, ranks
+
+    def ref_precept(self, intr, pose_world, init_pos):
+        """The REFERENCE's per-voxel method run for every voxel of this map (oracle/_ref/libprecept_ref.so)."""
+        out = np.zeros(self.n, dtype=POINT_DTYPE)
+        pw = _d16(pose_world)
+        ip = np.ascontiguousarray(init_pos, dtype=np.float64)
+        ok = ref_precept_lib().ref_precept(self._h, self.resolution, C.byref(intr), _ptr(pw, C.c_double), _ptr(ip, C.c_double),
+                                           out.ctypes.data_as(C.c_void_p))
+        return bool(ok), out
 
     def precept_threads(self, intr, pose_world, init_pos, max_range=1.0, num_of_thread=20):
         """precept with the reference's execution structure: one std::thread per voxel in batches of num_of_thread."""

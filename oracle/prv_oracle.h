@@ -5,16 +5,17 @@
  * import or execute this.  Allowed users: tests/, __graft_entry__.smoke(), bench.py's cpu_baseline
  * and `--impl reference` legs.
  *
- * PARITY: the camera functions (rs2_project_point_to_pixel / rs2_deproject_pixel_to_point) are PINNED bit for bit
- * against the reference's own code, compiled from where it lies into oracle/_ref/librs2_ref.so (`make -C oracle ref`,
- * tests/test_oracle_kat.py).  Everything else is PARITY UNPINNED: the reference (psc0628/NeRF-PRV) ships no tests,
- * golden vectors or fixtures for this path, and the rest of it cannot be compiled here (needs OctoMap 1.9.6,
- * PCL 1.9.1, VTK, Eigen 3.3.9, OpenCV, Gurobi, JsonCpp and Win32 headers; main.cpp:7 is ill-formed for g++).  The
- * oracle therefore restates, line by line, the reference code that exists (citations on every function) and the
- * published algorithm of the un-vendored third-party pieces (OctoMap 1.9.6 castRay / key maths,
- * octomath::Vector3, Eigen 3.3 fixed-size 4x4 inverse), and pins itself with analytic known-answer
- * tests, an independent Python restatement of castRay (tests/test_oracle_kat.py) and frozen golden vectors
- * (tests/golden/).
+ * PARITY: pinned bit for bit against the reference's OWN code, compiled from where it lies into oracle/_ref/
+ * (`make -C oracle ref`, tests/test_oracle_kat.py): the camera functions rs2_project_point_to_pixel /
+ * rs2_deproject_pixel_to_point (nothing but reference code), View::get_next_camera_pos (reference logic over our Eigen
+ * shim) and Perception_3D::precept_thread_process + project_pixel_to_ray_end (reference logic over Eigen / OctoMap / PCL
+ * shims, castRay answered by this oracle).  PARITY UNPINNED for what lives in the absent libraries: OctoMap 1.9.6
+ * castRay / key maths / leaf order and Eigen 3.3.9 rounding.  The reference (psc0628/NeRF-PRV) ships no tests, golden
+ * vectors or fixtures for this path, and as a whole cannot be compiled here (needs OctoMap, PCL 1.9.1, VTK, Eigen,
+ * OpenCV, Gurobi, JsonCpp and Win32 headers; main.cpp:7 is ill-formed for g++).  For those parts the oracle restates the
+ * published algorithm (OctoMap 1.9.6 castRay / key maths, octomath::Vector3, Eigen 3.3 fixed-size 4x4 inverse) and pins
+ * itself with analytic known-answer tests, an independent Python restatement of castRay (tests/test_oracle_kat.py) and
+ * frozen golden vectors (tests/golden/).
  *
  * All entry points are extern "C" so tests can drive them through ctypes.
  */

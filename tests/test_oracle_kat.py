@@ -374,3 +374,66 @@ def test_camera_maths_pinned_against_the_reference_code(orc, model):
                 assert a.tobytes() == b.tobytes(), (model, coeffs, px, depth, a, b)
             n_cmp += 1
     assert n_cmp == 1200
+
+
+def test_view_pose_logic_pinned_against_the_reference_view_class(prv, orc):
+    """oracle/_ref/libview_ref.so is the reference's OWN `class View` (View_Space.hpp:40-199: look-at frame, 71-step roll
+    search with its 1e-6 tie rule, final pose) compiled from /root/reference against oracle/ref_eigen_shim.hpp.  The
+    oracle's orc_view_pose and the host mirror's prv_host_view_pose must reproduce its pose bit for bit for every view of
+    the shipped hemisphere sets (pole view included) and for random camera / object placements."""
+    if orc.ref_view() is None:
+        pytest.skip("oracle/_ref/libview_ref.so not built and /root/reference not present")
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sets = json.load(open(os.path.join(root, "tests", "golden", "hemisphere_sets.json")))["sets"]
+    rng = np.random.default_rng(7)
+    n = 0
+    for name in ("3", "32", "100"):
+        pts = np.array([[float(c) for c in row] for row in sets[name]])
+        centre = np.array([0.013, -0.021, 0.004])
+        for p in pts:
+            init_pos = p * 0.3 + centre
+            ref = orc.ref_view_pose(init_pos, centre)
+            assert orc.view_pose(init_pos, centre).tobytes() == ref.tobytes(), (name, p)
+            assert prv.host_view_pose(init_pos, centre).tobytes() == ref.tobytes(), (name, p)
+            n += 1
+    for _ in range(60):  # a moved camera frame (now_camera_pose_world != I) and arbitrary positions
+        ang = rng.random(3) * 6.0
+        cz, sz, cy, sy, cx, sx = np.cos(ang[0]), np.sin(ang[0]), np.cos(ang[1]), np.sin(ang[1]), np.cos(ang[2]), np.sin(ang[2])
+        R = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]]) @ np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]]) @ np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+        now = np.eye(4)
+        now[:3, :3] = R
+        now[:3, 3] = rng.normal(size=3) * 0.2
+        centre = rng.normal(size=3) * 0.05
+        init_pos = centre + rng.normal(size=3) * 0.3
+        ref = orc.ref_view_pose(init_pos, centre, now)
+        assert orc.view_pose(init_pos, centre, now).tobytes() == ref.tobytes()
+        assert prv.host_view_pose(init_pos, centre, now).tobytes() == ref.tobytes()
+        n += 1
+    assert n == 3 + 32 + 100 + 60
+
+
+def test_per_voxel_logic_pinned_against_the_reference_precept_thread_process(prv, orc, synth):
+    """oracle/_ref/libprecept_ref.so runs the reference's OWN Perception_3D::precept_thread_process (main.cpp:238-284:
+    voxel -> camera frame -> distorting projection -> '>' bounds test -> int-truncated pixel -> project_pixel_to_ray_end
+    -> direction -> castRay -> colour lookup) for every voxel, compiled from /root/reference against Eigen / OctoMap / PCL
+    shims (castRay answered by the oracle).  orc_precept must give the identical cloud->points image."""
+    if orc.ref_precept_lib() is None:
+        pytest.skip("oracle/_ref/libprecept_ref.so not built and /root/reference not present")
+    w = synth.build_workload(prv, "C1", n_views=6, size=(640, 480))
+    m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
+    it = orc.make_intrinsics(w["intr"].width, w["intr"].height, w["intr"].fx, w["intr"].fy, w["intr"].ppx, w["intr"].ppy, w["intr"].model,
+                             list(w["intr"].coeffs))
+    seen = 0
+    for v in range(w["n_views"]):
+        ok_ref, ref = m.ref_precept(it, w["pose_world"][v], w["init_pos"][v])
+        ok, pts, _ = m.precept(it, w["pose_world"][v], w["init_pos"][v])
+        assert ok == ok_ref
+        for f in ("x", "y", "z", "r", "g", "b"):
+            assert np.array_equal(pts[f], ref[f]), (v, f)
+        seen += int(np.count_nonzero(ref["x"] != 0))
+    assert seen > 1000
+    # a view whose origin is outside the key range: "View out of map" -> all-zero cloud on both sides
+    ok_ref, ref = m.ref_precept(it, w["pose_world"][0], np.array([1.0e6, 0.0, 0.0]))
+    ok, pts, _ = m.precept(it, w["pose_world"][0], np.array([1.0e6, 0.0, 0.0]))
+    assert not ok_ref and not ok and not ref["x"].any() and not pts["x"].any()
