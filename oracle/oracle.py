@@ -155,6 +155,8 @@ def ref_view():
         L = C.CDLL(_REF_VIEW_PATH)
         d = C.c_double
         L.ref_view_get_next_camera_pos.argtypes = [C.POINTER(d), C.POINTER(d), C.POINTER(d), C.c_int, C.POINTER(d)]
+        L.ref_view_space.argtypes = [C.POINTER(C.c_float), C.c_ulonglong, C.POINTER(d), C.c_int, d, d, C.POINTER(d), C.POINTER(d), C.POINTER(d)]
+        L.ref_view_space.restype = C.c_int
         _ref_view = L
     return _ref_view
 
@@ -188,6 +190,18 @@ def ref_precept_lib():
         L.ref_precept.restype = C.c_int
         _ref_precept = L
     return _ref_precept
+
+
+def ref_view_space(points, sphere, view_space_radius, pt_norm):
+    """View_Space::get_view_space of the reference itself -> (center[3], predicted_size, init_pos[nv,3])."""
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    sph = np.ascontiguousarray(sphere, dtype=np.float64)
+    center = np.zeros(3)
+    size = C.c_double(0)
+    init = np.zeros((sph.shape[0], 3))
+    nv = ref_view().ref_view_space(_ptr(pts, C.c_float), pts.shape[0], _ptr(sph, C.c_double), sph.shape[0], pt_norm, view_space_radius,
+                                   _ptr(center, C.c_double), C.byref(size), _ptr(init, C.c_double))
+    return center, size.value, init[:nv].copy()
 
 
 def ref_project_point_to_pixel(intr, point):

@@ -437,3 +437,29 @@ def test_per_voxel_logic_pinned_against_the_reference_precept_thread_process(prv
     ok_ref, ref = m.ref_precept(it, w["pose_world"][0], np.array([1.0e6, 0.0, 0.0]))
     ok, pts, _ = m.precept(it, w["pose_world"][0], np.array([1.0e6, 0.0, 0.0]))
     assert not ok_ref and not ok and not ref["x"].any() and not pts["x"].any()
+
+
+def test_view_space_pinned_against_the_reference_get_view_space(prv, orc, synth):
+    """The reference's OWN View_Space::get_view_space (View_Space.hpp:517-558: sequential double centroid sums, farthest
+    point * 17/16, hemisphere rows scaled by view_space_radius / pt_norm with pt_norm taken from row 0, z < 0 rows skipped),
+    compiled from /root/reference over the Eigen shim, against the oracle and the host mirror: bit for bit."""
+    if orc.ref_view() is None:
+        pytest.skip("oracle/_ref/libview_ref.so not built and /root/reference not present")
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sets = json.load(open(os.path.join(root, "tests", "golden", "hemisphere_sets.json")))["sets"]
+    w = synth.build_workload(prv, "C1", n_views=4, size=(160, 120))
+    cloud = np.ascontiguousarray(w["cloud"], dtype=np.float32)
+    for name in ("3", "32", "100"):
+        sph = np.array([[float(c) for c in row] for row in sets[name]])
+        sph2 = sph.copy()
+        sph2[1, 2] = -0.25  # a row below the horizon is skipped
+        for s in (sph, sph2):
+            pt_norm = float(np.sqrt(s[0, 0] * s[0, 0] + (s[0, 1] * s[0, 1] + s[0, 2] * s[0, 2])))
+            rc, rs, ri = orc.ref_view_space(cloud, s, 0.3, pt_norm)
+            oc, os_, oi = orc.view_space(cloud, s, 0.3, pt_norm)
+            hc, hs, hi = prv.host_view_space(cloud, s, 0.3, pt_norm)
+            assert rc.tobytes() == oc.tobytes() == hc.tobytes()
+            assert rs == os_ == hs
+            assert ri.shape == oi.shape == hi.shape and ri.tobytes() == oi.tobytes() == hi.tobytes()
+            assert len(ri) == int((s[:, 2] >= 0).sum())
