@@ -65,8 +65,9 @@ __device__ __forceinline__ void write_hit(const CastParams& p, const ViewConst& 
 // kernel 1 (cull_kernel):   every pixel, loose float slab test against the grown AABB; survivors -> queue 1
 // kernel 2 (coarse_kernel): dense warps over queue 1, conservative coarse-brick walk; survivors -> queue 2
 // kernel 3 (march_kernel):  dense warps over queue 2, the exact castRay march
-// Kernels 2 and 3 run persistent blocks that pull 256-ray chunks of a flattened (view, chunk) list with an atomic
-// ticket, so expensive and cheap chunks balance across the 148 SMs and there is no partial last wave.
+// Kernels 2 and 3 are persistent: kernel 2's blocks pull 256-ray chunks, kernel 3's warps 32-ray chunks of a flattened
+// (view, chunk) list with an atomic ticket, so expensive and cheap chunks balance across the 148 SMs and there is no
+// partial last wave.
 
 // block-level stream compaction of `keep` lanes into a per-view queue: one atomic per block
 __device__ __forceinline__ void block_append(bool keep, uint32_t value, uint32_t* queue_view, uint32_t* count_view, uint32_t* s_woff, uint32_t* s_base) {
