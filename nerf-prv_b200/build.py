@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libprv_b200.so")
 SOURCES = ["prv_device.cu", "prv_host.cpp"]
-DEPS = ["prv_kernels.cuh", "kernels_common.cuh", "kernels_cast.cuh", "kernels_map.cuh", "kernels_greedy.cuh", "kernels_ensemble.cuh",
+DEPS = ["prv_kernels.cuh", "prv_view_const.hpp", "kernels_common.cuh", "kernels_cast.cuh", "kernels_map.cuh", "kernels_greedy.cuh", "kernels_ensemble.cuh",
         "kernels_splat.cuh", "prv_keys.hpp", "../host/prv_linalg.hpp", "../host/View_Space.hpp", "../host/Share_Data.hpp",
         "../host/Perception_3D.hpp", "../host/NBV_Net_Labeler.hpp", "../host/prv_io.hpp", "../host/prv_simulation.cpp", "../../include/prv.h"]
 

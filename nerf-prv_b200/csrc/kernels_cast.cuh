@@ -120,28 +120,9 @@ __global__ void __launch_bounds__(256, 8) cull_kernel(const CastParams p) {
         bool skip = false;
         const int region_x = rx0 + warp;
         if (!MASKED && region_x < regions_x && view_ok && fast && p.cam.region_cull_ok) {
-            const int plane = lane >> 3, corner = lane & 7;
-            // pyramid corners counter-clockwise in pixel space: (x0,y0) (x1,y0) (x1,y1) (x0,y1)
-            const float x0 = (float)((region_x << 5) - 2), x1 = (float)((region_x << 5) + 33);
-            const float y0 = (float)((region_y << 5) - 2), y1 = (float)((region_y << 5) + 33);
-            const float ax = (plane == 0 || plane == 3) ? x0 : x1, ay = (plane == 0 || plane == 1) ? y0 : y1;   // corner `plane`
-            const float bx = (plane == 0 || plane == 1) ? x1 : x0, by = (plane == 1 || plane == 2) ? y1 : y0;   // corner `plane+1`
-            float adx, ady, adz, bdx, bdy, bdz, cdx, cdy, cdz;
-            ray_direction_approx(p.cam, vc, ax, ay, adx, ady, adz);
-            ray_direction_approx(p.cam, vc, bx, by, bdx, bdy, bdz);
-            ray_direction_approx(p.cam, vc, 0.5f * (x0 + x1), 0.5f * (y0 + y1), cdx, cdy, cdz);  // interior reference ray
-            // plane through the origin containing corner rays a and b; orient the normal away from the interior ray
-            float nx = ady * bdz - adz * bdy, ny = adz * bdx - adx * bdz, nz = adx * bdy - ady * bdx;
-            const float sgn = (nx * cdx + ny * cdy + nz * cdz) > 0.0f ? -1.0f : 1.0f;
-            nx *= sgn; ny *= sgn; nz *= sgn;
-            const float inv_n = rsqrtf(fmaf(nx, nx, fmaf(ny, ny, nz * nz)));
-            const float px = ((corner & 1) ? p.map.bmax[0] : p.map.bmin[0]) - vc.origin[0];
-            const float py = ((corner & 2) ? p.map.bmax[1] : p.map.bmin[1]) - vc.origin[1];
-            const float pz = ((corner & 4) ? p.map.bmax[2] : p.map.bmin[2]) - vc.origin[2];
-            const float dist = fmaf(nx, px, fmaf(ny, py, nz * pz)) * inv_n;  // signed distance of the box corner to the plane
-            const bool outside = dist > 1.0e-5f;                             // float error here is ~1e-7 m
+            const bool outside = region_corner_outside(p.map, p.cam, vc, region_x, region_y, lane);
             const uint32_t bal = __ballot_sync(0xFFFFFFFFu, outside);
-            skip = ((bal & 0xFFu) == 0xFFu) || ((bal & 0xFF00u) == 0xFF00u) || ((bal & 0xFF0000u) == 0xFF0000u) || ((bal & 0xFF000000u) == 0xFF000000u);
+            skip = region_skip_from_ballot(bal);
         }
         if (lane == 0) s_skip[warp] = skip ? 1 : 0;
     }

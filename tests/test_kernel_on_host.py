@@ -1,0 +1,170 @@
+"""The per-ray device code of the ray-cast kernels (nerf-prv_b200/csrc/prv_kernels.cuh, unchanged) compiled with g++ and
+run on the CPU against the oracle (tests/cpp/kernel_on_host.cpp): exactness of the march variants, of the per-view
+fast-path proof and of the three conservative culls, without a GPU.  A checker only: the product has no CPU path."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STATS = ("rays", "region_culled", "loose_culled", "coarse_culled", "marched", "probes", "steps", "hits", "flags", "region_ok")
+
+
+@pytest.fixture(scope="module")
+def koh(tmp_path_factory):
+    out = tmp_path_factory.mktemp("koh") / "libkernel_on_host.so"
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-I/usr/local/cuda/include",
+                    "-o", str(out), os.path.join(ROOT, "tests", "cpp", "kernel_on_host.cpp")], check=True)
+    lib = C.CDLL(str(out))
+    assert lib.koh_num_stats() == len(STATS)
+    return lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def cast_dense(koh, w, v, variant, max_range=1.0, force_region_cull=-1, intr=None):
+    it = intr if intr is not None else w["intr"]
+    keys = np.ascontiguousarray(w["keys"], dtype=np.uint16)
+    rgb = np.ascontiguousarray(w["map_rgb"], dtype=np.uint8)
+    pw = np.ascontiguousarray(w["pose_world"][v], dtype=np.float64)
+    ip = np.ascontiguousarray(w["init_pos"][v], dtype=np.float64)
+    hit = np.zeros((it.height, it.width), dtype=np.uint32)
+    depth = np.zeros((it.height, it.width), dtype=np.float32)
+    st = np.zeros(len(STATS), dtype=np.uint64)
+    rc = koh.koh_cast_view_dense(_p(keys, C.c_uint16), _p(rgb, C.c_uint8), C.c_uint32(len(keys)), C.c_double(w["resolution"]), C.byref(it),
+                                 C.c_double(max_range), _p(pw, C.c_double), _p(ip, C.c_double), variant, force_region_cull,
+                                 _p(hit, C.c_uint32), _p(depth, C.c_float), _p(st, C.c_uint64))
+    assert rc == 0
+    return hit, depth, dict(zip(STATS, (int(x) for x in st)))
+
+
+def oracle_view(orc, w, v, max_range=1.0, intr=None):
+    it = intr if intr is not None else w["intr"]
+    m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
+    ointr = orc.make_intrinsics(it.width, it.height, it.fx, it.fy, it.ppx, it.ppy, it.model, list(it.coeffs))
+    st = orc.CastStats()
+    ok, r, d = m.cast_view_dense(ointr, w["pose_world"][v], w["init_pos"][v], max_range=max_range, stats=st)
+    return m, ointr, r, d, st.as_dict()
+
+
+@pytest.mark.parametrize("name,n_views,size", [("C1", 6, (320, 240)), ("C2", 4, (256, 192)), ("C1", 2, (640, 480))])
+def test_march_variants_and_culls_match_oracle(koh, prv, orc, synth, name, n_views, size):
+    w = synth.build_workload(prv, name, n_views=n_views, size=size)
+    region_culled = marched = 0
+    for v in range(n_views):
+        _, _, o_rank, o_depth, o_st = oracle_view(orc, w, v)
+        for variant in (0, 1, 2):
+            hit, depth, st = cast_dense(koh, w, v, variant)
+            assert np.array_equal(hit, o_rank), "%s view %d variant %d: first-hit ranks differ" % (name, v, variant)
+            assert np.array_equal(depth, o_depth)
+            assert st["hits"] == o_st["hits"] and st["rays"] == size[0] * size[1]
+            assert st["flags"] == 1 | 4  # in map, not in the object, fast-path proof holds at max_range 1.0
+            if variant == 1:  # FAST executes every in-AABB probe of the literal algorithm: S_in of the roofline
+                assert st["probes"] == o_st["probes_in"]
+            if variant == 2:
+                assert st["region_culled"] + st["loose_culled"] + st["coarse_culled"] + st["marched"] == st["rays"]
+                assert st["probes"] <= o_st["probes_in"]
+                region_culled += st["region_culled"]
+                marched += st["marched"]
+    assert marched > 0
+    if size[0] >= 640:  # at the bench resolution the shipped intrinsics pass the region-cull validation
+        assert region_culled > 0
+
+
+def test_full_size_view_of_the_bench_workload(koh, prv, orc, synth):
+    """One 640x480 view of C2 (BASELINE configs[1]) through the whole AXIS pipeline, and the stage split the DESIGN quotes."""
+    w = synth.build_workload(prv, "C2", n_views=100)
+    v = 37
+    _, _, o_rank, o_depth, o_st = oracle_view(orc, w, v)
+    hit, depth, st = cast_dense(koh, w, v, 2)
+    assert np.array_equal(hit, o_rank) and np.array_equal(depth, o_depth)
+    assert st["hits"] == o_st["hits"] > 10000
+    assert st["marched"] < 0.25 * st["rays"]  # the culls remove most of the image (3.55 M of 30.7 M rays marched)
+    assert st["marched"] >= st["hits"]
+
+
+def test_region_cull_never_removes_a_hit(koh, prv, orc, synth):
+    """The region-level cull (whole 32x32-pixel regions dismissed by four plane tests) on cameras it was validated for --
+    pin-hole, the shipped Brown-Conrady coefficients, an off-centre principal point, odd image sizes: a culled region may
+    only contain misses.  Where prv_set_camera's validation rejects the camera (coarse images under the same distortion:
+    a region then spans too much of the lens) the cull must stay off."""
+    total_culled = 0
+    for size, model, ppx_off, ppy_off, expect_ok in (((640, 480), 2, 0.0, 0.0, 1), ((640, 480), 0, 0.0, 0.0, 1), ((652, 470), 2, 41.0, -23.0, 1),
+                                                     ((640, 480), 4, -30.0, 17.0, 1), ((200, 136), 2, 0.0, 0.0, 0)):
+        w = synth.build_workload(prv, "C1", n_views=8, size=size)
+        it = w["intr"]
+        it.model = model
+        it.ppx += ppx_off
+        it.ppy += ppy_off
+        for v in (0, 5):
+            _, _, o_rank, o_depth, _ = oracle_view(orc, w, v)
+            hit, depth, st = cast_dense(koh, w, v, 2)
+            assert st["region_ok"] == expect_ok, (size, model)
+            assert np.array_equal(hit, o_rank) and np.array_equal(depth, o_depth), (size, model, v)
+            if expect_ok:
+                assert st["region_culled"] > 0
+                hit_off, _, st_off = cast_dense(koh, w, v, 2, force_region_cull=0)
+                assert np.array_equal(hit_off, hit) and st_off["region_culled"] == 0
+                assert st_off["marched"] == st["marched"]  # the region cull only removes rays the slab test would remove too
+            else:
+                assert st["region_culled"] == 0
+            total_culled += st["region_culled"]
+    assert total_culled > 0
+
+
+def test_max_range_disables_the_fast_path(koh, prv, orc, synth):
+    """maxRange inside the scene: the per-view proof must fail (flags without kViewFastOk) and the literal march must agree."""
+    w = synth.build_workload(prv, "C1", n_views=3, size=(96, 72))
+    for mr in (0.29, 0.33):
+        for v in range(3):
+            _, _, o_rank, o_depth, _ = oracle_view(orc, w, v, max_range=mr)
+            for variant in (0, 1, 2):
+                hit, depth, st = cast_dense(koh, w, v, variant, max_range=mr)
+                assert st["flags"] == 1, "fast-path proof must fail when maxRange can cut a ray short"
+                assert np.array_equal(hit, o_rank) and np.array_equal(depth, o_depth)
+                if variant == 2:
+                    assert st["marched"] == st["rays"]  # no cull may run without the proof
+
+
+def test_view_in_object_and_out_of_map(koh, prv, orc, synth):
+    w = synth.build_workload(prv, "C1", n_views=2, size=(64, 48))
+    res = w["resolution"]
+    k = w["keys"][len(w["keys"]) // 2].astype(np.float64)
+    inside = (k - 32768 + 0.5) * res  # centre of an occupied voxel: "view in the object" (main.cpp:263-267)
+    w["init_pos"][0] = inside
+    w["init_pos"][1] = np.array([1.0e6, 0.0, 0.0])  # coordToKeyChecked fails: "View out of map" (main.cpp:139)
+    for v, flags in ((0, 1 | 2), (1, 0)):
+        hit, depth, st = cast_dense(koh, w, v, 2)
+        assert st["flags"] & 3 == flags & 3
+        assert np.all(hit == 0xFFFFFFFF) and np.all(depth == 0) and st["rays"] == 0
+
+
+def test_precept_matches_oracle(koh, prv, orc, synth):
+    """Voxel-driven mode (Perception_3D::precept): projection, truncated pixel (== W / == H pass), per-voxel gather."""
+    w = synth.build_workload(prv, "C1", n_views=4, size=(320, 240))
+    it = w["intr"]
+    m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
+    ointr = orc.make_intrinsics(it.width, it.height, it.fx, it.fy, it.ppx, it.ppy, it.model, list(it.coeffs))
+    keys = np.ascontiguousarray(w["keys"], dtype=np.uint16)
+    rgb = np.ascontiguousarray(w["map_rgb"], dtype=np.uint8)
+    for v in range(4):
+        ok, o_pts, o_ranks = m.precept(ointr, w["pose_world"][v], w["init_pos"][v])
+        pts = np.zeros(len(keys), dtype=prv.POINT_DTYPE)  # pcl::PointXYZRGB image, 32 B
+        ranks = np.zeros(len(keys), dtype=np.uint32)
+        in_map = C.c_int(0)
+        pw = np.ascontiguousarray(w["pose_world"][v], dtype=np.float64)
+        ip = np.ascontiguousarray(w["init_pos"][v], dtype=np.float64)
+        rc = koh.koh_precept(_p(keys, C.c_uint16), _p(rgb, C.c_uint8), C.c_uint32(len(keys)), C.c_double(w["resolution"]), C.byref(it),
+                             C.c_double(1.0), _p(pw, C.c_double), _p(ip, C.c_double), pts.ctypes.data_as(C.c_void_p), _p(ranks, C.c_uint32),
+                             C.byref(in_map))
+        assert rc == 0 and in_map.value == 1 and ok
+        assert np.array_equal(ranks, o_ranks)
+        for fld in ("x", "y", "z", "r", "g", "b"):
+            assert np.array_equal(pts[fld], o_pts[fld]), fld
+        assert np.all(pts["w"] == 1.0) and np.all(pts["a"] == 255)
+        assert (ranks != orc.NONE).sum() > 100
