@@ -111,6 +111,11 @@ const char* prv_last_error(const prv_ctx* ctx); /* ctx may be NULL: last create 
 int         prv_device_info(prv_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, uint64_t* mem_bytes);
 int         prv_sync(prv_ctx* ctx);
 int         prv_set_variant(prv_ctx* ctx, int variant);
+/* Optional second level of the conservative brick cull in front of the exact march (variant AXIS): a finer occupancy grid
+ * (cells of `cell` = 1, 2 or 4 voxels, dilated by one voxel like the 8-voxel bricks) that proves more through-the-AABB
+ * misses without marching them.  Results are identical with and without it; it only moves work between kernels.
+ * 0 = off (default).  Takes effect at the next prv_set_map / prv_set_map_from_cloud. */
+int         prv_set_fine_cull(prv_ctx* ctx, int cell);
 
 /* ---------------------------------------------------------------- host-side logic (pure host, no device)
  * One implementation of the reference's pose / view-space / map-insertion arithmetic for every caller. */

@@ -248,7 +248,8 @@ __device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint3
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 8) coarse_kernel(const CastParams p) {
+template <bool FINE>
+__device__ __forceinline__ void coarse_body(const CastParams& p) {
     __shared__ ViewConst s_vc;
     __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
     __shared__ uint32_t s_woff[8];
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(256, 8) coarse_kernel(const CastParams p) {
             } else {
                 float dx, dy, dz;
                 ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
-                keep = !coarse_miss(p.map, vc, dx, dy, dz);
+                keep = FINE ? !coarse_miss_fine(p.map, vc, dx, dy, dz) : !coarse_miss(p.map, vc, dx, dy, dz);
             }
             if (!keep && p.pix_hit) {
                 const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
@@ -303,6 +304,9 @@ __global__ void __launch_bounds__(256, 8) coarse_kernel(const CastParams p) {
         block_append(keep, pid, p.queue2 + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
     }
 }
+__global__ void __launch_bounds__(256, 8) coarse_kernel(const CastParams p) { coarse_body<false>(p); }
+// with the optional second cull level (prv_set_fine_cull): the nested walk needs ~50 registers, so 4 blocks/SM
+__global__ void __launch_bounds__(256, 4) coarse_fine_kernel(const CastParams p) { coarse_body<true>(p); }
 
 // Persistent WARPS: every warp pulls 32-ray chunks of the flattened (view, chunk) list with its own atomic ticket and
 // shares nothing with the other warps of its block after the chunk-prefix table is built -- no block barrier in the loop

@@ -74,7 +74,7 @@ struct prv_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int variant = PRV_VARIANT_AXIS;
-    int occ_coarse = 0, occ_march = 0, occ_greedy = 0;
+    int occ_coarse = 0, occ_coarse_fine = 0, occ_march = 0, occ_greedy = 0;
     uint32_t occ_greedy_words = 0;
     bool greedy_persistent = false;
     // PRV_GREEDY_CLUSTER=0 forces the grid-barrier kernel (the fallback for tables larger than one cluster's shared memory)
@@ -91,6 +91,8 @@ struct prv_ctx {
     double resolution = 0;
     int lo[3] = {0, 0, 0}, n[3] = {0, 0, 0};
     DevBuf d_coarse;
+    DevBuf d_fine;   // optional second cull level (prv_set_fine_cull)
+    int fine_k = 0;  // cell size requested for the NEXT prv_set_map; ctx->map.fine_k is what the resident map carries
     DevBuf d_bitmap, d_bitmap_pad, d_prefix, d_leaf_of_raster, d_keys, d_rgb, d_tilesum;
     std::vector<uint16_t> h_keys;
 
@@ -415,8 +417,10 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
             p.tickets = ptr<uint32_t>(ctx->d_tickets) + 2 * li;
             if (ctx->occ_coarse == 0) {  // persistent grids = exactly one resident wave
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_coarse, coarse_kernel, 256, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_coarse_fine, coarse_fine_kernel, 256, 0);
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march, march_kernel<kMarchBlock, kMarchMinBlocks>, kMarchBlock, 0);
                 ctx->occ_coarse = std::max(1, ctx->occ_coarse);
+                ctx->occ_coarse_fine = std::max(1, ctx->occ_coarse_fine);
                 ctx->occ_march = std::max(1, ctx->occ_march);
             }
             {
@@ -426,7 +430,10 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
                     cull_kernel<true><<<rgrid, 256, 0, ctx->stream>>>(p);
                 else
                     cull_kernel<false><<<rgrid, 256, 0, ctx->stream>>>(p);
-                coarse_kernel<<<(uint32_t)(ctx->sm_count * ctx->occ_coarse), 256, 0, ctx->stream>>>(p);
+                if (p.map.fine_k > 0)
+                    coarse_fine_kernel<<<(uint32_t)(ctx->sm_count * ctx->occ_coarse_fine), 256, 0, ctx->stream>>>(p);
+                else
+                    coarse_kernel<<<(uint32_t)(ctx->sm_count * ctx->occ_coarse), 256, 0, ctx->stream>>>(p);
             }
             Span s(ctx, K_MARCH, 1);
             march_kernel<kMarchBlock, kMarchMinBlocks><<<(uint32_t)(ctx->sm_count * ctx->occ_march), kMarchBlock, 0, ctx->stream>>>(p);
@@ -644,6 +651,10 @@ int prv_create(prv_ctx** out, int device) {
     for (auto& s : ctx->slots) cudaEventCreate(&s);
     cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
     if (const char* e = getenv("PRV_GREEDY_CLUSTER")) ctx->greedy_no_cluster = atoi(e) == 0;
+    if (const char* e = getenv("PRV_FINE_CULL")) {  // same as prv_set_fine_cull before the first prv_set_map
+        const int k = atoi(e);
+        if (k == 1 || k == 2 || k == 4) ctx->fine_k = k;
+    }
     *out = ctx;
     return PRV_OK;
 }
@@ -653,7 +664,7 @@ void prv_destroy(prv_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     prv_comm_destroy(ctx);
-    DevBuf* bufs[] = {&ctx->d_tilesum, &ctx->d_coarse, &ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
+    DevBuf* bufs[] = {&ctx->d_tilesum, &ctx->d_coarse, &ctx->d_fine, &ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
                       &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_tickets, &ctx->d_arrive, &ctx->d_ens_images, &ctx->d_ens_terms, &ctx->d_ens_scores, &ctx->d_row_of_id_all, &ctx->d_ing_xyz, &ctx->d_ing_rgb, &ctx->d_ing_k0,
                       &ctx->d_ing_k1, &ctx->d_ing_v0, &ctx->d_ing_v1, &ctx->d_ing_pos, &ctx->d_ing_tmp, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
                       &ctx->d_voxel_pix, &ctx->d_voxel_hit, &ctx->d_points, &ctx->d_best, &ctx->d_cov[0], &ctx->d_cov[1], &ctx->d_all_rows,
@@ -694,6 +705,13 @@ int prv_set_variant(prv_ctx* ctx, int variant) {
     return PRV_OK;
 }
 
+int prv_set_fine_cull(prv_ctx* ctx, int cell) {
+    if (!ctx) return PRV_ERR_INVALID;
+    if (cell != 0 && cell != 1 && cell != 2 && cell != 4) return fail(ctx, PRV_ERR_INVALID, "prv_set_fine_cull: cell must be 0 (off), 1, 2 or 4 voxels, got %d", cell);
+    ctx->fine_k = cell;
+    return PRV_OK;
+}
+
 // keys/rgb: host copies in leaf order.  device_ready: d_keys / d_rgb already hold the same data (GPU ingest path).
 static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, uint32_t N, double resolution, bool device_ready) {
     if (!ctx) return PRV_ERR_INVALID;
@@ -727,8 +745,16 @@ static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, 
     int nc[3];
     for (int a = 0; a < 3; a++) nc[a] = (n[a] + kCoarse - 1) / kCoarse;
     const size_t coarse_words = ((size_t)nc[0] * nc[1] * nc[2] + 31) / 32 + 1;
+    const int fine_k = ctx->fine_k;
+    int nf[3] = {0, 0, 0};
+    size_t fine_words = 0;
+    if (fine_k > 0) {
+        for (int a = 0; a < 3; a++) nf[a] = (n[a] + fine_k - 1) / fine_k;
+        fine_words = ((size_t)nf[0] * nf[1] * nf[2] + 31) / 32 + 1;
+    }
     int rc;
     if ((rc = ensure(ctx, ctx->d_coarse, coarse_words * 4))) return rc;
+    if (fine_k > 0 && (rc = ensure(ctx, ctx->d_fine, fine_words * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_bitmap_pad, pad_words * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_bitmap, nwords * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_prefix, nwords * 4))) return rc;
@@ -746,6 +772,7 @@ static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, 
     }
     CU(cudaEventRecord(ctx->ev_copy, ctx->stream));  // the caller's buffers are free once this has passed
     CU(cudaMemsetAsync(ctx->d_coarse.p, 0, coarse_words * 4, ctx->stream));
+    if (fine_k > 0) CU(cudaMemsetAsync(ctx->d_fine.p, 0, fine_words * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_bitmap_pad.p, 0, pad_words * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_bitmap.p, 0, nwords * 4, ctx->stream));
     {
@@ -766,8 +793,12 @@ static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, 
         mb.prefix = ptr<uint32_t>(ctx->d_prefix);
         mb.leaf_of_raster = ptr<uint32_t>(ctx->d_leaf_of_raster);
         mb.keys = ptr<uint16_t>(ctx->d_keys);
-        Span sp(ctx, K_OTHER, 5);
+        mb.fine = fine_k > 0 ? ptr<uint32_t>(ctx->d_fine) : nullptr;
+        for (int a = 0; a < 3; a++) mb.nf[a] = nf[a];
+        mb.fine_k = fine_k;
+        Span sp(ctx, K_OTHER, fine_k > 0 ? 6 : 5);
         map_scatter_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(mb);
+        if (fine_k > 0) map_fine_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(mb);
         map_shell_kernel<<<(uint32_t)((pad_rows + 255) / 256), 256, 0, ctx->stream>>>(mb);
         const uint32_t ntiles = (uint32_t)((nwords + kPrefixTile - 1) / kPrefixTile);
         map_tilesum_kernel<<<ntiles, kPrefixThreads, 0, ctx->stream>>>(mb, ptr<uint32_t>(ctx->d_tilesum));
@@ -803,6 +834,9 @@ static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, 
     }
     ctx->map.coarse = ptr<uint32_t>(ctx->d_coarse);
     for (int a = 0; a < 3; a++) ctx->map.nc[a] = nc[a];
+    ctx->map.fine = fine_k > 0 ? ptr<uint32_t>(ctx->d_fine) : nullptr;
+    for (int a = 0; a < 3; a++) ctx->map.nf[a] = nf[a];
+    ctx->map.fine_k = fine_k;
     ctx->map.pad_row_log2 = row_log2;
     ctx->map.pad_bit_offset = (uint32_t)slack_bits;
     for (int a = 0; a < 3; a++) {

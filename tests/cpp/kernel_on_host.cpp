@@ -74,13 +74,13 @@ namespace {
 // the HBM tables of one map, built on the host from the documented layout
 struct HostMap {
     DevMap m{};
-    std::vector<uint32_t> bitmap, pad, coarse, prefix, leaf_of_raster;
+    std::vector<uint32_t> bitmap, pad, coarse, fine, prefix, leaf_of_raster;
     std::vector<uint16_t> keys;
     std::vector<uint8_t> rgb;
     ViewSetup setup{};
 };
 
-bool build_map(HostMap& hm, const uint16_t* keys, const uint8_t* rgb, uint32_t N, double resolution, double max_range) {
+bool build_map(HostMap& hm, const uint16_t* keys, const uint8_t* rgb, uint32_t N, double resolution, double max_range, int fine_k = 0) {
     if (N == 0) return false;
     hm.keys.assign(keys, keys + 3 * (size_t)N);
     if (rgb) hm.rgb.assign(rgb, rgb + 3 * (size_t)N); else hm.rgb.assign(3 * (size_t)N, 0);
@@ -124,6 +124,9 @@ bool build_map(HostMap& hm, const uint16_t* keys, const uint8_t* rgb, uint32_t N
             for (int c0 = 0; c0 < m.n[0] + 2; c0++)
                 if (c0 == 0 || c0 == m.n[0] + 1 || c1 == 0 || c1 == m.n[1] + 1 || c2 == 0 || c2 == m.n[2] + 1) set_pad(c0, c1, c2);
     hm.coarse.assign(((size_t)m.nc[0] * m.nc[1] * m.nc[2] + 31) / 32 + 1, 0u);
+    m.fine_k = fine_k;  // optional second cull level (prv_set_fine_cull)
+    for (int a = 0; a < 3; a++) m.nf[a] = fine_k > 0 ? (m.n[a] + fine_k - 1) / fine_k : 0;
+    if (fine_k > 0) hm.fine.assign(((size_t)m.nf[0] * m.nf[1] * m.nf[2] + 31) / 32 + 1, 0u);
     for (uint32_t i = 0; i < N; i++) {
         const int q[3] = {keys[3 * i] - lo[0], keys[3 * i + 1] - lo[1], keys[3 * i + 2] - lo[2]};
         hm.bitmap[((size_t)q[2] * m.n[1] + q[1]) * m.wx + (q[0] >> 5)] |= 1u << (q[0] & 31);
@@ -136,6 +139,10 @@ bool build_map(HostMap& hm, const uint16_t* keys, const uint8_t* rgb, uint32_t N
                     if (p0 < 0 || p1 < 0 || p2 < 0 || p0 >= m.n[0] || p1 >= m.n[1] || p2 >= m.n[2]) continue;
                     const uint32_t c = (uint32_t)(((p2 / kCoarse) * m.nc[1] + p1 / kCoarse) * m.nc[0] + p0 / kCoarse);
                     hm.coarse[c >> 5] |= 1u << (c & 31);
+                    if (fine_k > 0) {
+                        const uint32_t f = (uint32_t)(((p2 / fine_k) * m.nf[1] + p1 / fine_k) * m.nf[0] + p0 / fine_k);
+                        hm.fine[f >> 5] |= 1u << (f & 31);
+                    }
                 }
     }
     hm.prefix.assign(hm.bitmap.size(), 0u);
@@ -154,6 +161,7 @@ bool build_map(HostMap& hm, const uint16_t* keys, const uint8_t* rgb, uint32_t N
     m.bitmap = hm.bitmap.data();
     m.bitmap_pad = hm.pad.data();
     m.coarse = hm.coarse.data();
+    m.fine = fine_k > 0 ? hm.fine.data() : nullptr;
     m.prefix = hm.prefix.data();
     m.leaf_of_raster = hm.leaf_of_raster.data();
     m.keys = hm.keys.data();
@@ -203,7 +211,7 @@ void axis_pixel(const HostMap& hm, const DevCam& cam, const ViewConst& vc, int p
             st[S_LOOSE_CULLED]++;
             return;
         }
-        if (coarse_miss(hm.m, vc, dx, dy, dz)) {
+        if (hm.m.fine_k > 0 ? coarse_miss_fine(hm.m, vc, dx, dy, dz) : coarse_miss(hm.m, vc, dx, dy, dz)) {
             st[S_COARSE_CULLED]++;
             return;
         }
@@ -229,14 +237,15 @@ float hit_depth(const HostMap& hm, const ViewConst& vc, const CastResult& res) {
 extern "C" {
 
 // Dense cast of one view.  variant: 0 PLAIN, 1 FAST (raycast_kernel), 2 AXIS pipeline (cull / coarse / march kernels).
-// force_region_cull: -1 = as prv_set_camera decides, 0 / 1 = force off / on.
+// force_region_cull: -1 = as prv_set_camera decides, 0 / 1 = force off / on.  fine_k: prv_set_fine_cull (0 = off).
 // hit_rank, depth: [H][W]; stats: S_N counters.  Returns 0, or -1 for bad input.
 int koh_cast_view_dense(const uint16_t* keys, const uint8_t* rgb, uint32_t N, double resolution, const prv_intrinsics* intr, double max_range,
-                        const double* pose_world, const double* init_pos, int variant, int force_region_cull, uint32_t* hit_rank, float* depth,
-                        uint64_t* stats) {
+                        const double* pose_world, const double* init_pos, int variant, int force_region_cull, int fine_k, uint32_t* hit_rank,
+                        float* depth, uint64_t* stats) {
     HostMap hm;
     if (!keys || !intr || !pose_world || !init_pos || !hit_rank || !depth || !stats) return -1;
-    if (!build_map(hm, keys, rgb, N, resolution, max_range)) return -1;
+    if (fine_k != 0 && fine_k != 1 && fine_k != 2 && fine_k != 4) return -1;
+    if (!build_map(hm, keys, rgb, N, resolution, max_range, fine_k)) return -1;
     const DevCam cam = make_cam(*intr, max_range, force_region_cull);
     ViewConst vc;
     std::memset(&vc, 0, sizeof(vc));
