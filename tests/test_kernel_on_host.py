@@ -211,3 +211,15 @@ def test_reproduces_the_counters_the_b200_recorded(koh, prv, synth, name, n_view
     assert abs(tot["marched"] - rec["marched"]) <= 4
     assert abs(tot["probes"] - rec["probes_in"]) <= 2e-6 * rec["probes_in"]
     assert abs(tot["steps"] - rec["steps"]) <= 2e-6 * rec["steps"]
+
+
+def test_roofline_numerator_s_in_of_the_bench_workload(koh, prv, synth):
+    """bench.py's roofline numerator is 4 B x S_in (+ 8 B per ray, + per-view terms), S_in = in-AABB probes of the literal
+    algorithm, counted on the device with variant FAST.  The same code on the CPU counts the same S_in for C2."""
+    import json
+    rec = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_C2_n1.json")))
+    w = synth.build_workload(prv, "C2")
+    s_in = sum(cast_dense(koh, w, v, 1)[2]["probes"] for v in range(w["n_views"]))
+    assert s_in == rec["roofline"]["s_in_probes"] == 313642529
+    per_ray = 4 * s_in + 8 * rec["cast_stats"]["rays"]
+    assert per_ray < rec["roofline"]["cast_pipeline"]["algorithmic_bytes"] < per_ray * 1.05  # + bitmap and row per view
