@@ -89,6 +89,31 @@ __device__ __forceinline__ void block_append(bool keep, uint32_t value, uint32_t
     __syncthreads();  // s_woff / s_base are reused by the next chunk
 }
 
+// same, two parallel queues (pixel, fine cell)
+__device__ __forceinline__ void block_append2(bool keep, uint32_t v1, uint32_t v2, uint32_t* q1, uint32_t* q2, uint32_t* count_view, uint32_t* s_woff,
+                                              uint32_t* s_base) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+    if (lane == 0) s_woff[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t tot = 0;
+        for (int w = 0; w < 8; w++) {
+            const uint32_t c = s_woff[w];
+            s_woff[w] = tot;
+            tot += c;
+        }
+        *s_base = tot ? atomicAdd(count_view, tot) : 0u;
+    }
+    __syncthreads();
+    if (keep) {
+        const uint32_t pos = *s_base + s_woff[warp] + __popc(bal & ((1u << lane) - 1u));
+        q1[pos] = v1;
+        q2[pos] = v2;
+    }
+    __syncthreads();
+}
+
 // One block per kCullRegions consecutive 32x32-pixel regions of one row of one view (blockIdx = (region group, region
 // row, view)): the view constants are fetched once and the region tests of the group run side by side (one warp each),
 // so the ~1.5 us of serial latency at the start of a block (constants from L2, barrier, region test) is paid once per
@@ -284,7 +309,7 @@ __device__ __forceinline__ void coarse_body(const CastParams& p) {
         const uint32_t count = p.qcount[view];
         const uint32_t idx = (g - s_prefix[vl]) * 256u + threadIdx.x;
         bool keep = false;
-        uint32_t pid = 0;
+        uint32_t pid = 0, cell = kNone;
         if (idx < count) {
             pid = p.queue[(size_t)view * p.queue_cap + idx];
             const int py = (int)(pid >> 16), px = (int)(pid & 0xFFFFu);
@@ -293,7 +318,7 @@ __device__ __forceinline__ void coarse_body(const CastParams& p) {
             } else {
                 float dx, dy, dz;
                 ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
-                keep = FINE ? !coarse_miss_fine(p.map, vc, dx, dy, dz) : !coarse_miss(p.map, vc, dx, dy, dz);
+                keep = FINE ? !coarse_miss_fine(p.map, vc, dx, dy, dz, cell) : !coarse_miss(p.map, vc, dx, dy, dz);
             }
             if (!keep && p.pix_hit) {
                 const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
@@ -301,7 +326,10 @@ __device__ __forceinline__ void coarse_body(const CastParams& p) {
                 if (p.pix_depth) p.pix_depth[o] = 0.0f;
             }
         }
-        block_append(keep, pid, p.queue2 + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
+        if (FINE && p.queue2b)
+            block_append2(keep, pid, cell, p.queue2 + (size_t)view * p.queue_cap, p.queue2b + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
+        else
+            block_append(keep, pid, p.queue2 + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
     }
 }
 __global__ void __launch_bounds__(256, 8) coarse_kernel(const CastParams p) { coarse_body<false>(p); }
@@ -315,8 +343,8 @@ __global__ void __launch_bounds__(256, 4) coarse_fine_kernel(const CastParams p)
 // hidden (un-prefetched warp tickets had measured 6 % slower than block tickets).  Measured on C2: 56 registers / 32 warps
 // per SM (no spills) 0.514 ms, 48 / 40 (16 B spilled) 0.521 ms, 40 / 48 (88 B spilled) 0.530 ms.
 constexpr int kMarchBlock = 256, kMarchMinBlocks = 4;
-template <int BS, int MINB>
-__global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
+template <int BS, int MINB, bool ENTRY>
+__device__ __forceinline__ void march_body(const CastParams& p) {
     __shared__ ViewConst s_vcw[BS / 32];
     __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
     build_chunk_prefix(p.qcount2 + p.view_base, p.nviews, s_prefix, 32u);
@@ -350,6 +378,7 @@ __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
         const uint32_t idx = (g - s_prefix[vl]) * 32u + (uint32_t)lane;
         if (idx < count) {
             const uint32_t packed = p.queue2[(size_t)view * p.queue_cap + idx];
+            const uint32_t cell = ENTRY ? p.queue2b[(size_t)view * p.queue_cap + idx] : kNone;
             const int py = (int)(packed >> 16), px = (int)(packed & 0xFFFFu);
             const uint32_t pid = (uint32_t)py * (uint32_t)p.GW + (uint32_t)px;
             CastResult res;
@@ -363,7 +392,7 @@ __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
             if (ray_init(vc, p.map.resolution, dx, dy, dz, r)) {
                 if (!(vc.flags & kViewFastOk))
                     march_plain(p.map, p.cam, vc, r, res);
-                else
+                else if (!ENTRY || cell == kNone || !march_axis_box(p.map, vc, r, cell, res))
                     march_axis(p.map, vc, r, res);
             }
             write_hit(p, vc, view, pid, res);
@@ -375,6 +404,11 @@ __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
     }
     if (cur_view != 0xFFFFFFFFu) warp_commit_stats(p.stats + 4 * (size_t)cur_view, c_probes, c_hits, c_steps);
 }
+template <int BS, int MINB>
+__global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) { march_body<BS, MINB, false>(p); }
+// optional: the exact march starts at the fine cell found by coarse_fine_kernel (prv_set_fine_cull(cell, 1))
+template <int BS, int MINB>
+__global__ void __launch_bounds__(BS, MINB) march_entry_kernel(const CastParams p) { march_body<BS, MINB, true>(p); }
 
 // ---- PLAIN / FAST variants: one kernel, one thread per pixel of a 32x8 tile ----------------------------------------
 template <int VARIANT, bool MASKED>

@@ -74,7 +74,7 @@ struct prv_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int variant = PRV_VARIANT_AXIS;
-    int occ_coarse = 0, occ_coarse_fine = 0, occ_march = 0, occ_greedy = 0;
+    int occ_coarse = 0, occ_coarse_fine = 0, occ_march = 0, occ_march_entry = 0, occ_greedy = 0;
     uint32_t occ_greedy_words = 0;
     bool greedy_persistent = false;
     // PRV_GREEDY_CLUSTER=0 forces the grid-barrier kernel (the fallback for tables larger than one cluster's shared memory)
@@ -93,6 +93,7 @@ struct prv_ctx {
     DevBuf d_coarse;
     DevBuf d_fine;   // optional second cull level (prv_set_fine_cull)
     int fine_k = 0;  // cell size requested for the NEXT prv_set_map; ctx->map.fine_k is what the resident map carries
+    bool fine_entry = false;  // start the exact march at the fine cell that stopped the nested walk (needs fine_k > 0)
     DevBuf d_bitmap, d_bitmap_pad, d_prefix, d_leaf_of_raster, d_keys, d_rgb, d_tilesum;
     std::vector<uint16_t> h_keys;
 
@@ -114,7 +115,7 @@ struct prv_ctx {
     uint32_t id_space = 0;
 
     // cast outputs
-    DevBuf d_queue, d_qcount, d_queue2, d_tickets;
+    DevBuf d_queue, d_qcount, d_queue2, d_queue2b, d_tickets;
     DevBuf d_bitsets, d_counts, d_stats, d_pix_hit, d_pix_depth, d_mask, d_voxel_pix, d_voxel_hit, d_points;
     int last_mode = -1;
     bool have_pixels = false;
@@ -400,6 +401,12 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
         p.queue2 = ptr<uint32_t>(ctx->d_queue2);
         p.qcount2 = ptr<uint32_t>(ctx->d_qcount) + V;
         p.queue_cap = ctx->pix_stride;
+        // fine-cell entry needs the packed cell coordinates to fit (kFineCellBits per axis)
+        const bool entry = ctx->fine_entry && ctx->map.fine_k > 0 && std::max(ctx->map.nf[0], std::max(ctx->map.nf[1], ctx->map.nf[2])) <= (1 << kFineCellBits);
+        if (entry) {
+            if ((rc = ensure(ctx, ctx->d_queue2b, (size_t)V * ctx->pix_stride * 4))) return rc;
+            p.queue2b = ptr<uint32_t>(ctx->d_queue2b);
+        }
     }
     const uint32_t tiles = (uint32_t)(((p.GW + 31) / 32) * ((p.GH + 7) / 8));
     const uint32_t vstep = ctx->variant == PRV_VARIANT_AXIS ? (uint32_t)kMaxViewsPerLaunch : 32768u;
@@ -419,6 +426,8 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_coarse, coarse_kernel, 256, 0);
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_coarse_fine, coarse_fine_kernel, 256, 0);
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march, march_kernel<kMarchBlock, kMarchMinBlocks>, kMarchBlock, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march_entry, march_entry_kernel<kMarchBlock, kMarchMinBlocks>, kMarchBlock, 0);
+                ctx->occ_march_entry = std::max(1, ctx->occ_march_entry);
                 ctx->occ_coarse = std::max(1, ctx->occ_coarse);
                 ctx->occ_coarse_fine = std::max(1, ctx->occ_coarse_fine);
                 ctx->occ_march = std::max(1, ctx->occ_march);
@@ -436,7 +445,10 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
                     coarse_kernel<<<(uint32_t)(ctx->sm_count * ctx->occ_coarse), 256, 0, ctx->stream>>>(p);
             }
             Span s(ctx, K_MARCH, 1);
-            march_kernel<kMarchBlock, kMarchMinBlocks><<<(uint32_t)(ctx->sm_count * ctx->occ_march), kMarchBlock, 0, ctx->stream>>>(p);
+            if (p.queue2b)
+                march_entry_kernel<kMarchBlock, kMarchMinBlocks><<<(uint32_t)(ctx->sm_count * ctx->occ_march_entry), kMarchBlock, 0, ctx->stream>>>(p);
+            else
+                march_kernel<kMarchBlock, kMarchMinBlocks><<<(uint32_t)(ctx->sm_count * ctx->occ_march), kMarchBlock, 0, ctx->stream>>>(p);
         } else {
             Span s(ctx, K_CAST, 1);
             if (ctx->variant == PRV_VARIANT_PLAIN)
@@ -652,8 +664,11 @@ int prv_create(prv_ctx** out, int device) {
     cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
     if (const char* e = getenv("PRV_GREEDY_CLUSTER")) ctx->greedy_no_cluster = atoi(e) == 0;
     if (const char* e = getenv("PRV_FINE_CULL")) {  // same as prv_set_fine_cull before the first prv_set_map
-        const int k = atoi(e);
-        if (k == 1 || k == 2 || k == 4) ctx->fine_k = k;
+        const int k = atoi(e);  // "1", "2", "4"; "-1", "-2", "-4": the same with the march starting at the fine cell
+        if (k == 1 || k == 2 || k == 4 || k == -1 || k == -2 || k == -4) {
+            ctx->fine_k = k < 0 ? -k : k;
+            ctx->fine_entry = k < 0;
+        }
     }
     *out = ctx;
     return PRV_OK;
@@ -665,7 +680,7 @@ void prv_destroy(prv_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     prv_comm_destroy(ctx);
     DevBuf* bufs[] = {&ctx->d_tilesum, &ctx->d_coarse, &ctx->d_fine, &ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
-                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_tickets, &ctx->d_arrive, &ctx->d_ens_images, &ctx->d_ens_terms, &ctx->d_ens_scores, &ctx->d_row_of_id_all, &ctx->d_ing_xyz, &ctx->d_ing_rgb, &ctx->d_ing_k0,
+                      &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_queue2b, &ctx->d_tickets, &ctx->d_arrive, &ctx->d_ens_images, &ctx->d_ens_terms, &ctx->d_ens_scores, &ctx->d_row_of_id_all, &ctx->d_ing_xyz, &ctx->d_ing_rgb, &ctx->d_ing_k0,
                       &ctx->d_ing_k1, &ctx->d_ing_v0, &ctx->d_ing_v1, &ctx->d_ing_pos, &ctx->d_ing_tmp, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
                       &ctx->d_voxel_pix, &ctx->d_voxel_hit, &ctx->d_points, &ctx->d_best, &ctx->d_cov[0], &ctx->d_cov[1], &ctx->d_all_rows,
                       &ctx->d_all_ids, &ctx->d_cloud_xyz, &ctx->d_cloud_rgb, &ctx->d_corner, &ctx->d_rgba, &ctx->d_depth_img, &ctx->d_flush};
@@ -705,10 +720,11 @@ int prv_set_variant(prv_ctx* ctx, int variant) {
     return PRV_OK;
 }
 
-int prv_set_fine_cull(prv_ctx* ctx, int cell) {
+int prv_set_fine_cull(prv_ctx* ctx, int cell, int enter_at_cell) {
     if (!ctx) return PRV_ERR_INVALID;
     if (cell != 0 && cell != 1 && cell != 2 && cell != 4) return fail(ctx, PRV_ERR_INVALID, "prv_set_fine_cull: cell must be 0 (off), 1, 2 or 4 voxels, got %d", cell);
     ctx->fine_k = cell;
+    ctx->fine_entry = cell != 0 && enter_at_cell != 0;
     return PRV_OK;
 }
 

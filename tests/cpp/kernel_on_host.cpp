@@ -196,14 +196,15 @@ DevCam make_cam(const prv_intrinsics& it, double max_range, int force_region_cul
     return c;
 }
 
-enum { S_RAYS = 0, S_REGION_CULLED, S_LOOSE_CULLED, S_COARSE_CULLED, S_MARCHED, S_PROBES, S_STEPS, S_HITS, S_FLAGS, S_REGION_OK, S_N };
+enum { S_RAYS = 0, S_REGION_CULLED, S_LOOSE_CULLED, S_COARSE_CULLED, S_MARCHED, S_PROBES, S_STEPS, S_HITS, S_FLAGS, S_REGION_OK, S_BOX_ENTRIES, S_BOX_FALLBACKS, S_N };
 
 // one pixel through stages 1b..3 of the AXIS pipeline (cull_kernel's per-pixel part, coarse_kernel, march_kernel)
-void axis_pixel(const HostMap& hm, const DevCam& cam, const ViewConst& vc, int px, int py, CastResult& res, uint64_t* st) {
+void axis_pixel(const HostMap& hm, const DevCam& cam, const ViewConst& vc, int px, int py, CastResult& res, uint64_t* st, bool entry = false) {
     res.rank = kNone;
     res.steps = res.probes = 0;
     res.k0 = res.k1 = res.k2 = 0;
     const bool fast = (vc.flags & kViewFastOk) != 0;
+    uint32_t cell = kNone;  // what coarse_fine_kernel hands to march_entry_kernel through queue2b
     if (fast) {
         float dx, dy, dz;
         ray_direction_approx(cam, vc, (float)px, (float)py, dx, dy, dz);
@@ -211,7 +212,7 @@ void axis_pixel(const HostMap& hm, const DevCam& cam, const ViewConst& vc, int p
             st[S_LOOSE_CULLED]++;
             return;
         }
-        if (hm.m.fine_k > 0 ? coarse_miss_fine(hm.m, vc, dx, dy, dz) : coarse_miss(hm.m, vc, dx, dy, dz)) {
+        if (hm.m.fine_k > 0 ? coarse_miss_fine(hm.m, vc, dx, dy, dz, cell) : coarse_miss(hm.m, vc, dx, dy, dz)) {
             st[S_COARSE_CULLED]++;
             return;
         }
@@ -221,10 +222,17 @@ void axis_pixel(const HostMap& hm, const DevCam& cam, const ViewConst& vc, int p
     float dx, dy, dz;
     ray_direction(cam, vc, px, py, dx, dy, dz);
     if (ray_init(vc, hm.m.resolution, dx, dy, dz, r)) {
-        if (!fast)
+        if (!fast) {
             march_plain(hm.m, cam, vc, r, res);
-        else
+        } else if (entry && cell != kNone) {  // march_body<ENTRY = true>
+            st[S_BOX_ENTRIES]++;
+            if (!march_axis_box(hm.m, vc, r, cell, res)) {
+                st[S_BOX_FALLBACKS]++;
+                march_axis(hm.m, vc, r, res);
+            }
+        } else {
             march_axis(hm.m, vc, r, res);
+        }
     }
 }
 
@@ -237,15 +245,17 @@ float hit_depth(const HostMap& hm, const ViewConst& vc, const CastResult& res) {
 extern "C" {
 
 // Dense cast of one view.  variant: 0 PLAIN, 1 FAST (raycast_kernel), 2 AXIS pipeline (cull / coarse / march kernels).
-// force_region_cull: -1 = as prv_set_camera decides, 0 / 1 = force off / on.  fine_k: prv_set_fine_cull (0 = off).
+// force_region_cull: -1 = as prv_set_camera decides, 0 / 1 = force off / on.  fine_k, fine_entry: prv_set_fine_cull (0 = off).
 // hit_rank, depth: [H][W]; stats: S_N counters.  Returns 0, or -1 for bad input.
 int koh_cast_view_dense(const uint16_t* keys, const uint8_t* rgb, uint32_t N, double resolution, const prv_intrinsics* intr, double max_range,
-                        const double* pose_world, const double* init_pos, int variant, int force_region_cull, int fine_k, uint32_t* hit_rank,
-                        float* depth, uint64_t* stats) {
+                        const double* pose_world, const double* init_pos, int variant, int force_region_cull, int fine_k, int fine_entry,
+                        uint32_t* hit_rank, float* depth, uint64_t* stats) {
     HostMap hm;
     if (!keys || !intr || !pose_world || !init_pos || !hit_rank || !depth || !stats) return -1;
     if (fine_k != 0 && fine_k != 1 && fine_k != 2 && fine_k != 4) return -1;
     if (!build_map(hm, keys, rgb, N, resolution, max_range, fine_k)) return -1;
+    // as cast_impl: the packed cell coordinates must fit
+    const bool entry = fine_entry && fine_k > 0 && std::max(hm.m.nf[0], std::max(hm.m.nf[1], hm.m.nf[2])) <= (1 << kFineCellBits);
     const DevCam cam = make_cam(*intr, max_range, force_region_cull);
     ViewConst vc;
     std::memset(&vc, 0, sizeof(vc));
@@ -303,7 +313,7 @@ int koh_cast_view_dense(const uint16_t* keys, const uint8_t* rgb, uint32_t N, do
             for (int py = ry << 5; py < y1; py++)
                 for (int px = rx << 5; px < x1; px++) {
                     CastResult res;
-                    axis_pixel(hm, cam, vc, px, py, res, stats);
+                    axis_pixel(hm, cam, vc, px, py, res, stats, entry);
                     stats[S_PROBES] += res.probes;
                     stats[S_STEPS] += res.steps;
                     if (res.rank != kNone) stats[S_HITS]++;

@@ -18,8 +18,8 @@ def test_fine_cull_is_exact_and_marches_fewer_rays(prv, orc, synth, name, n_view
     w = synth.build_workload(prv, name, n_views=n_views, size=size)
     c = prv.Context(0)
     try:
-        def run(cell):
-            c.set_fine_cull(cell)
+        def run(cell, entry=False):
+            c.set_fine_cull(cell, entry)
             c.set_map(w["keys"], w["map_rgb"], w["resolution"])
             c.set_camera(w["intr"], 1.0)
             bits, counts, hit, depth = c.cast_views(w["pose_world"], w["init_pos"], mode=prv.MODE_DENSE, want_hit_rank=True, want_depth=True)
@@ -43,9 +43,16 @@ def test_fine_cull_is_exact_and_marches_fewer_rays(prv, orc, synth, name, n_view
             assert got[4]["hits"] == base[4]["hits"] and got[4]["rays"] == base[4]["rays"]
             assert got[4]["hits"] <= got[4]["marched"] <= prev
             prev = got[4]["marched"]
+            # the exact march started at the first set fine cell: same results, same DDA steps, fewer probes
+            ent = run(cell, True)
+            for a, b in zip(ent[:4], base[:4]):
+                assert np.array_equal(a, b), "fine cull %d with entry at the cell changed a result" % cell
+            assert ent[5].tolist() == base[5].tolist() and ent[6].tolist() == base[6].tolist()
+            assert ent[4]["marched"] == got[4]["marched"] and ent[4]["steps"] == got[4]["steps"] and ent[4]["hits"] == base[4]["hits"]
+            assert ent[4]["probes_in"] < got[4]["probes_in"]
         assert prev < base[4]["marched"]
         # voxel-driven mode goes through the same coarse kernel
-        c.set_fine_cull(1)
+        c.set_fine_cull(1, True)
         c.set_map(w["keys"], w["map_rgb"], w["resolution"])
         c.set_camera(w["intr"], 1.0)
         bv1, cv1, hv1, _ = c.cast_views(w["pose_world"], w["init_pos"], mode=prv.MODE_VOXEL, want_hit_rank=True)

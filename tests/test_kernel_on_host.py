@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-STATS = ("rays", "region_culled", "loose_culled", "coarse_culled", "marched", "probes", "steps", "hits", "flags", "region_ok")
+STATS = ("rays", "region_culled", "loose_culled", "coarse_culled", "marched", "probes", "steps", "hits", "flags", "region_ok", "box_entries", "box_fallbacks")
 
 
 @pytest.fixture(scope="module")
@@ -27,7 +27,7 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def cast_dense(koh, w, v, variant, max_range=1.0, force_region_cull=-1, intr=None, fine_k=0):
+def cast_dense(koh, w, v, variant, max_range=1.0, force_region_cull=-1, intr=None, fine_k=0, fine_entry=False):
     it = intr if intr is not None else w["intr"]
     keys = np.ascontiguousarray(w["keys"], dtype=np.uint16)
     rgb = np.ascontiguousarray(w["map_rgb"], dtype=np.uint8)
@@ -37,7 +37,7 @@ def cast_dense(koh, w, v, variant, max_range=1.0, force_region_cull=-1, intr=Non
     depth = np.zeros((it.height, it.width), dtype=np.float32)
     st = np.zeros(len(STATS), dtype=np.uint64)
     rc = koh.koh_cast_view_dense(_p(keys, C.c_uint16), _p(rgb, C.c_uint8), C.c_uint32(len(keys)), C.c_double(w["resolution"]), C.byref(it),
-                                 C.c_double(max_range), _p(pw, C.c_double), _p(ip, C.c_double), variant, force_region_cull, fine_k,
+                                 C.c_double(max_range), _p(pw, C.c_double), _p(ip, C.c_double), variant, force_region_cull, fine_k, 1 if fine_entry else 0,
                                  _p(hit, C.c_uint32), _p(depth, C.c_float), _p(st, C.c_uint64))
     assert rc == 0
     return hit, depth, dict(zip(STATS, (int(x) for x in st)))
@@ -132,6 +132,11 @@ def test_fine_cull_level_is_exact_and_culls_more(koh, prv, orc, synth, name, siz
             assert st["marched"] <= prev  # a finer grid never keeps more rays
             assert st["region_culled"] == base["region_culled"] and st["loose_culled"] == base["loose_culled"]
             prev = st["marched"]
+            # ... and with the exact march starting at the fine cell: same results, same DDA steps, fewer probes
+            hit_e, depth_e, st_e = cast_dense(koh, w, v, 2, fine_k=fine_k, fine_entry=True)
+            assert np.array_equal(hit_e, o_rank) and np.array_equal(depth_e, o_depth), (name, v, fine_k, "entry")
+            assert st_e["marched"] == st["marched"] and st_e["steps"] == st["steps"] and st_e["probes"] < st["probes"]
+            assert st_e["box_entries"] > 0 and st_e["box_fallbacks"] == 0
         assert prev < base["marched"]  # cells of one voxel prove more misses than the 8-voxel bricks alone
 
 
@@ -301,9 +306,10 @@ def test_random_tie_prone_scenes(koh, prv, orc):
     for case in range(200):
         w, max_range = _random_scene(rng, prv, perms)
         _, _, o_rank, o_depth, _ = oracle_view(orc, w, 0, max_range=max_range)
-        for variant, fine_k in ((0, 0), (1, 0), (2, 0), (2, 1), (2, 2), (2, 4)):
-            hit, depth, st = cast_dense(koh, w, 0, variant, max_range=max_range, fine_k=fine_k)
-            assert np.array_equal(hit, o_rank) and np.array_equal(depth, o_depth), "scene %d variant %d fine cull %d" % (case, variant, fine_k)
+        for variant, fine_k, entry in ((0, 0, 0), (1, 0, 0), (2, 0, 0), (2, 1, 0), (2, 2, 0), (2, 4, 0), (2, 1, 1), (2, 2, 1), (2, 4, 1)):
+            hit, depth, st = cast_dense(koh, w, 0, variant, max_range=max_range, fine_k=fine_k, fine_entry=bool(entry))
+            assert np.array_equal(hit, o_rank) and np.array_equal(depth, o_depth), "scene %d variant %d fine cull %d entry %d" % (case, variant, fine_k, entry)
+            assert st["box_fallbacks"] == 0
         hits += int((o_rank != 0xFFFFFFFF).sum())
         fast += 1 if st["flags"] & 4 else 0
         in_object += 1 if st["flags"] & 2 else 0
