@@ -5,8 +5,8 @@
 
 Prints, for the default pipeline and for candidate changes, the modelled warp-instructions of the coarse and march
 kernels.  Calibration: the per-trip instruction counts below were read off the round-1 sm_100a SASS; the fixed per-warp
-cost is set so that the default C2 total equals ncu's 416.9 M warp-instructions for march_kernel
-(profiles/r1_ncu_source_lines_march.txt).
+costs are set so that the default C2 totals equal ncu's 416.9 M warp-instructions for march_kernel and 94.5 M for
+coarse_kernel (profiles/r1_ncu_source_lines_march.txt, profiles/r1_ncu_full_summary.md).
 """
 import ctypes as C
 import os
@@ -25,8 +25,8 @@ CMP_ITER = 4.0       # while (t < thr) { t += d; n++; }
 INNER4 = 81.0        # one trip of the 4-probes-in-flight in-AABB loop
 INNER_EXIT = 25.0    # decode of the stopping cell
 WALK_ITER = 14.0     # one float cell step of the brick walks
-COARSE_FIX = 120.0   # per coarse-kernel warp chunk: ticket, view prefix, direction, slab of the grown box, compaction
-MARCH_FIX = None     # calibrated below
+COARSE_FIX = None    # per coarse-kernel warp: ticket, view prefix, direction, slab of the grown box, cell set-up, compaction (calibrated)
+MARCH_FIX = None     # per march-kernel warp: set-up, windows, epilogue (calibrated)
 
 
 def load():
@@ -87,10 +87,10 @@ def march_cost(recs, extra_approach=None, nprobe=None, fixed=0.0):
     return dict(total=approach + inner + fixed * warps, approach=approach, inner=inner, fixed=fixed * warps, warps=warps, lane_eff=lane_eff)
 
 
-def coarse_cost(walk_iters):
+def coarse_cost(walk_iters, fixed=None):
     """warp-instructions of the coarse kernel: 256-ray chunks = 8 consecutive warps of queue 1."""
     wt = warp_max(walk_iters.astype(np.int64))
-    return float((WALK_ITER * wt + COARSE_FIX).sum())
+    return float((WALK_ITER * wt + (COARSE_FIX if fixed is None else fixed)).sum())
 
 
 def main():
@@ -100,19 +100,23 @@ def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "C2"
     stride = int(sys.argv[2]) if len(sys.argv) > 2 else (1 if name in ("C1", "C2") else 16)
     lib = load()
-    global MARCH_FIX
-    # calibration on C2 (all 100 views): fixed per-warp cost such that the default total = 416.9 M
-    cal_file = "/tmp/march_model_fix.txt"
+    global MARCH_FIX, COARSE_FIX
+    # calibration on C2 (all 100 views): fixed per-warp costs such that the default totals = ncu's 416.9 M / 94.5 M
+    cal_file = "/tmp/march_model_fix2.txt"
     if os.path.exists(cal_file):
-        MARCH_FIX = float(open(cal_file).read())
+        MARCH_FIX, COARSE_FIX = (float(x) for x in open(cal_file).read().split())
     else:
         wc = synth.build_workload(prv, "C2")
         pv = collect(lib, wc, range(wc["n_views"]))
         var = sum(march_cost(r[k])["total"] for r, k in pv)
         warps = sum(march_cost(r[k])["warps"] for r, k in pv)
-        MARCH_FIX = (416.9e6 - var) / warps
-        open(cal_file, "w").write(repr(float(MARCH_FIX)))
-        print("calibration: C2 loops %.1f M warp-instr over %d warps -> fixed %.0f per warp (set-up, windows, epilogue, ticket)" % (var / 1e6, warps, MARCH_FIX))
+        MARCH_FIX = float((416.9e6 - var) / warps)
+        cvar = sum(coarse_cost(r["walk8"], 0.0) for r, _ in pv)
+        cwarps = sum((len(r) + 31) // 32 for r, _ in pv)
+        COARSE_FIX = float((94.47e6 - cvar) / cwarps)
+        open(cal_file, "w").write("%r %r" % (MARCH_FIX, COARSE_FIX))
+        print("calibration on C2: march loops %.1f M over %d warps -> fixed %.0f per warp; coarse walk %.1f M over %d warps -> fixed %.0f per warp" %
+              (var / 1e6, warps, MARCH_FIX, cvar / 1e6, cwarps, COARSE_FIX))
     w = synth.build_workload(prv, name)
     views = list(range(0, w["n_views"], stride))
     pv = collect(lib, w, views)
