@@ -140,6 +140,11 @@ int prv_host_normalize_cloud(float* pts_xyz, uint64_t P, double target_size, dou
 int prv_host_build_map(const float* pts_xyz, const uint8_t* rgb, uint64_t P, double resolution,
                        uint16_t* keys_out, uint8_t* rgb_out, uint32_t* n_out);
 
+/* Leaf-order check of a key table: keys must be in strictly ascending begin_leafs() (Morton) order, as prv_set_map requires
+ * (main.cpp:116-121).  *first_bad_out = index of the first key that is not above its predecessor, or N when the table is in
+ * order.  (prv_set_map runs this itself; BMI2 pdep when the CPU has it.) */
+int prv_host_check_leaf_order(const uint16_t* keys /* N x 3 */, uint32_t N, uint32_t* first_bad_out);
+
 /* ---------------------------------------------------------------- device inputs */
 /* ground_truth_model (Share_Data.hpp:258,458): occupied leaf keys in leaf order + voxel colours (may be NULL). */
 int prv_set_map(prv_ctx* ctx, const uint16_t* keys /* N x 3 */, const uint8_t* rgb /* N x 3 */, uint32_t N,

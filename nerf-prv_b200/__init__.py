@@ -95,6 +95,7 @@ def lib():
         "prv_host_view_space": (i, [P(f), u64, P(d), i, d, d, P(d), P(d), P(d), P(i)]),
         "prv_host_normalize_cloud": (i, [P(f), u64, d, P(d)]),
         "prv_host_build_map": (i, [P(f), P(u8), u64, d, P(u16), P(u8), P(u32)]),
+        "prv_host_check_leaf_order": (i, [P(u16), u32, P(u32)]),
         "prv_set_map": (i, [vp, P(u16), P(u8), u32, d]),
         "prv_set_map_from_cloud": (i, [vp, P(f), P(u8), u64, d]),
         "prv_get_map": (i, [vp, P(u16), P(u8)]),
@@ -234,6 +235,16 @@ def host_build_map(points, rgb, resolution):
     if rc:
         raise PrvError(rc, "prv_host_build_map")
     return keys[:n.value].copy(), out_rgb[:n.value].copy()
+
+
+def host_check_leaf_order(keys):
+    """Index of the first key that is not above its predecessor in leaf (Morton) order, or len(keys) when in order."""
+    k = np.ascontiguousarray(keys, dtype=np.uint16).reshape(-1, 3)
+    bad = C.c_uint32(0)
+    rc = lib().prv_host_check_leaf_order(_p(k, C.c_uint16), k.shape[0], C.byref(bad))
+    if rc:
+        raise PrvError(rc, "prv_host_check_leaf_order")
+    return int(bad.value)
 
 
 def view_poses(init_pos, object_center):

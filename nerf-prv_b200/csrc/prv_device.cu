@@ -733,18 +733,16 @@ static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, 
     if (!ctx) return PRV_ERR_INVALID;
     if (!keys || N == 0 || !(resolution > 0)) return fail(ctx, PRV_ERR_INVALID, "prv_set_map: null/empty map or bad resolution");
     CU(cudaSetDevice(ctx->device));
-    // leaf order must be strictly ascending Morton (begin_leafs order, no duplicates)
-    uint64_t prev = 0;
+    // leaf order must be strictly ascending Morton (begin_leafs order, no duplicates); host loop, GPU idle meanwhile
+    uint32_t first_bad = N;
+    prv_host_check_leaf_order(keys, N, &first_bad);
+    if (first_bad < N) return fail(ctx, PRV_ERR_INVALID, "prv_set_map: keys are not in strict leaf (Morton) order at index %u", first_bad);
     int lo[3] = {65536, 65536, 65536}, hi[3] = {-1, -1, -1};
-    for (uint32_t i = 0; i < N; i++) {
-        const uint64_t c = prv::morton_code(keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]);
-        if (i && c <= prev) return fail(ctx, PRV_ERR_INVALID, "prv_set_map: keys are not in strict leaf (Morton) order at index %u", i);
-        prev = c;
+    for (uint32_t i = 0; i < N; i++)
         for (int a = 0; a < 3; a++) {
-            lo[a] = std::min(lo[a], (int)keys[3 * i + a]);
-            hi[a] = std::max(hi[a], (int)keys[3 * i + a]);
+            lo[a] = std::min(lo[a], (int)keys[3 * (size_t)i + a]);
+            hi[a] = std::max(hi[a], (int)keys[3 * (size_t)i + a]);
         }
-    }
     int n[3];
     for (int a = 0; a < 3; a++) n[a] = hi[a] - lo[a] + 1;
     const int wx = (n[0] + 31) / 32;

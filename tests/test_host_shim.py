@@ -106,3 +106,44 @@ def test_synthetic_workloads_are_deterministic(prv, synth):
     assert np.array_equal(a["keys"], b["keys"]) and np.array_equal(a["pose_world"], b["pose_world"])
     assert 15000 < len(a["keys"]) < 25000 and abs(a["predicted_size"] - 0.10) < 1e-6
     assert not np.any(np.all(a["cloud_rgb"] == 255, axis=1))
+
+
+def test_leaf_order_check(prv, synth):
+    """prv_host_check_leaf_order (what prv_set_map validates with; pdep fast path on BMI2 CPUs): agrees with a plain
+    Morton-code comparison on a real key table, on duplicates, on swaps at every scale and on the empty table."""
+    w = synth.build_workload(prv, "C1", n_views=1, size=(32, 24))
+    keys = np.ascontiguousarray(w["keys"], dtype=np.uint16)
+    n = len(keys)
+    assert prv.host_check_leaf_order(keys) == n
+    assert prv.host_check_leaf_order(keys[:0]) == 0 and prv.host_check_leaf_order(keys[:1]) == 1
+
+    def code(k):
+        c = 0
+        for b in range(16):
+            c |= ((int(k[0]) >> b) & 1) << (3 * b) | ((int(k[1]) >> b) & 1) << (3 * b + 1) | ((int(k[2]) >> b) & 1) << (3 * b + 2)
+        return c
+
+    def reference(kk):
+        for i in range(1, len(kk)):
+            if code(kk[i]) <= code(kk[i - 1]):
+                return i
+        return len(kk)
+
+    rng = np.random.default_rng(5)
+    for trial in range(60):
+        kk = keys[: int(rng.integers(2, 400))].copy()
+        i = int(rng.integers(0, len(kk) - 1))
+        mode = trial % 3
+        if mode == 0:
+            kk[i + 1] = kk[i]                      # duplicate
+        elif mode == 1:
+            kk[[i, i + 1]] = kk[[i + 1, i]]        # neighbours swapped
+        else:
+            kk[i] = rng.integers(0, 65536, size=3)  # random key anywhere in the 16-bit cube
+        assert prv.host_check_leaf_order(kk) == reference(kk), (trial, mode, i)
+    # full-range keys: the top bits of every axis take part in the order
+    big = rng.integers(0, 65536, size=(300, 3)).astype(np.uint16)
+    order = np.argsort([code(k) for k in big], kind="stable")
+    assert prv.host_check_leaf_order(big[order]) in (300, reference(big[order]))
+    assert prv.host_check_leaf_order(big[order]) == reference(big[order])
+    assert prv.host_check_leaf_order(big) == reference(big)
