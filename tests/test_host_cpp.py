@@ -262,3 +262,42 @@ def test_prv_simulation_mode3_end_to_end(tmp_path, prv, orc, synth, binary):
     # other modes are refused, unknown objects fail cleanly
     assert subprocess.run([drv, str(cfg)], input="21\nobj_a\n-1\n", capture_output=True, text=True).returncode == 2
     assert subprocess.run([drv, str(cfg)], input="3\nmissing_obj\n-1\n", capture_output=True, text=True).returncode == 3
+
+
+def test_yaml_values_equal_what_opencv_filestorage_reads(host_check, tmp_path, synth):
+    """The reference reads DefaultConfiguration.yaml with cv::FileStorage (Share_Data.hpp:339-401).  OpenCV's own parser is
+    importable here (cv2, used as a checker only): every value the host mirror's parser produces must equal what
+    cv::FileStorage returns for the same key, narrowed to the type of the reference's field (float intrinsics, double
+    resolutions, int counters) -- on the test file with the reference's syntax quirks and on the shipped file when present."""
+    cv2 = pytest.importorskip("cv2")
+    files = [str(write_env(tmp_path, synth))]
+    if os.path.exists("/root/reference/PRV_simulation/DefaultConfiguration.yaml"):
+        files.append("/root/reference/PRV_simulation/DefaultConfiguration.yaml")
+    # host_check name -> (yaml key, type of the reference's field)
+    fields = {"pre_path": ("pre_path", str), "model_path": ("model_path", str), "viewspace_path": ("viewspace_path", str),
+              "num_of_thread": ("num_of_thread", int), "ground_truth_resolution": ("ground_truth_resolution", float),
+              "octomap_resolution": ("octomap_resolution", float), "coverage_view_num_max": ("coverage_view_num_max", int),
+              "coverage_view_num_add": ("coverage_view_num_add", int), "points_size_cloud": ("points_size_cloud", int),
+              "num_of_max_iteration": ("num_of_max_iteration", int), "view_space_radius": ("view_space_radius", float),
+              "width": ("color_width", int), "height": ("color_height", int), "fx": ("color_fx", np.float32), "fy": ("color_fy", np.float32),
+              "ppx": ("color_ppx", np.float32), "ppy": ("color_ppy", np.float32), "model": ("color_model", int),
+              "c0": ("color_k1", np.float32), "c1": ("color_k2", np.float32), "c2": ("color_k3", np.float32), "c3": ("color_p1", np.float32),
+              "c4": ("color_p2", np.float32), "depth_scale": ("depth_scale", float), "object_pixel_rate": ("object_pixel_rate", float),
+              "is_shape_net": ("is_shape_net", int), "show": ("show", int), "ensemble_num": ("ensemble_num", int),
+              "ray_casting_aabb_scale": ("ray_casting_aabb_scale", int), "n_steps": ("n_steps", int)}
+    for path in files:
+        r = results(subprocess.run([host_check, "yaml", path], capture_output=True, text=True, check=True).stdout)
+        fs = cv2.FileStorage(path, cv2.FILE_STORAGE_READ)
+        assert fs.isOpened()
+        for name, (key, typ) in fields.items():
+            node = fs.getNode(key)
+            assert not node.isNone(), key
+            if typ is str:
+                assert r[name] == node.string(), (path, key)
+            elif typ is int:
+                assert int(r[name]) == int(node.real()), (path, key)
+            elif typ is np.float32:
+                assert np.float32(float(r[name])) == np.float32(node.real()), (path, key)
+            else:
+                assert float(r[name]) == float(node.real()), (path, key)
+        fs.release()
