@@ -61,3 +61,44 @@ def test_gpu_reproduces_golden(case, prv, synth, ctx):
     ctx.set_cloud(w["cloud"], w["cloud_rgb"])
     rgba, sdepth = ctx.render_views(w["pose_world"][1:2], 5)
     assert sha(rgba[0]) == case["splat_rgba_sha"] and sha(sdepth[0]) == case["splat_depth_sha"]
+
+
+# ---- full-size BASELINE workloads (tests/golden/golden_full.json, frozen from the CPU oracle by make_golden_full.py) ----------
+FULL = json.load(open(os.path.join(HERE, "golden", "golden_full.json")))["cases"]
+ROOT = os.path.dirname(HERE)
+
+
+@pytest.mark.parametrize("case", FULL, ids=[c["name"] for c in FULL])
+def test_recorded_b200_run_matches_the_full_size_oracle_vectors(case):
+    """profiles/r1_bench_C{1,2}_n1.json are the bench lines the round-1 B200 runs printed.  What they record of the results --
+    hit count, greedy sequence, coverage rate, S_in -- must be what the oracle computes for the whole workload."""
+    rec = json.load(open(os.path.join(ROOT, "profiles", "r1_bench_%s_n1.json" % case["name"])))
+    assert rec["cast_stats"]["rays"] == case["rays"] and rec["cast_stats"]["hits"] == case["hits"]
+    assert rec["greedy_seq"] == case["greedy_seq"] and rec["greedy_len"] == len(case["greedy_seq"])
+    assert rec["coverage_rate"] == sum(case["greedy_gain"]) / case["full_voxels"]
+    assert rec["roofline"]["s_in_probes"] == case["s_in"]
+    assert rec["config"]["voxels"] == case["full_voxels"] and rec["config"]["views"] == case["n_views"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", FULL, ids=[c["name"] for c in FULL])
+def test_gpu_reproduces_full_size_golden(case, prv, synth, ctx):
+    """BASELINE C1 / C2 at full size through the C ABI: every view's first-hit ranks, depths and coverage row, the counts and
+    the greedy sequence against the frozen oracle vectors -- the region cull included, which only full-size images exercise."""
+    w = synth.build_workload(prv, case["name"])
+    assert sha(w["keys"]) == case["keys_sha"] and sha(w["pose_world"]) == case["pose_world_sha"] and sha(w["init_pos"]) == case["init_pos_sha"]
+    ctx.set_variant(prv.VARIANT_AXIS)
+    ctx.set_map(w["keys"], w["map_rgb"], w["resolution"])
+    ctx.set_camera(w["intr"], 1.0)
+    assert ctx.full_voxels == case["full_voxels"] and ctx.words == case["words"]
+    bits, counts, hit, depth = ctx.cast_views(w["pose_world"], w["init_pos"], mode=prv.MODE_DENSE, want_hit_rank=True, want_depth=True)
+    assert counts.tolist() == case["counts"]
+    for v in range(case["n_views"]):
+        assert sha(hit[v]) == case["hit_sha"][v], "first-hit ranks of view %d" % v
+        assert sha(depth[v]) == case["depth_sha"][v], "depths of view %d" % v
+        assert sha(bits[v]) == case["row_sha"][v], "coverage row of view %d" % v
+    st = ctx.get_cast_stats()
+    assert st["rays"] == case["rays"] and st["hits"] == case["hits"]
+    ctx.greedy_async(0, 64)
+    seq, gain, cov = ctx.get_greedy(64)
+    assert seq.tolist() == case["greedy_seq"] and gain.tolist() == case["greedy_gain"] and sha(cov) == case["covered_sha"]

@@ -314,3 +314,21 @@ def test_random_tie_prone_scenes(koh, prv, orc):
         fast += 1 if st["flags"] & 4 else 0
         in_object += 1 if st["flags"] & 2 else 0
     assert hits > 5000 and 100 < fast < 200 and in_object > 5  # hits, both march paths and the in-object case all occurred
+
+
+def test_full_size_golden_views(koh, prv, synth):
+    """A few views of the full-size oracle vectors (tests/golden/golden_full.json) through the host-compiled per-ray code, with
+    and without the opt-in cull level / later march start."""
+    import hashlib
+    import json
+    cases = {c["name"]: c for c in json.load(open(os.path.join(ROOT, "tests", "golden", "golden_full.json")))["cases"]}
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+    for name, views in (("C1", (0, 17)), ("C2", (0, 42, 99))):
+        w = synth.build_workload(prv, name)
+        for v in views:
+            for fine_k, entry in ((0, False), (1, True), (2, True)):
+                hit, depth, st = cast_dense(koh, w, v, 2, fine_k=fine_k, fine_entry=entry)
+                assert sha(hit) == cases[name]["hit_sha"][v] and sha(depth) == cases[name]["depth_sha"][v], (name, v, fine_k, entry)
