@@ -30,8 +30,11 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def compute(name):
+def compute(name, views=None):
+    """views: None = every view (coverage counts, greedy); else only those views of the workload (hashes per listed view)."""
     w = synth.build_workload(prv, name)
+    if views is not None:
+        return compute_sample(name, w, views)
     m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
     it = orc.make_intrinsics(w["intr"].width, w["intr"].height, w["intr"].fx, w["intr"].fy, w["intr"].ppx, w["intr"].ppy, w["intr"].model,
                              list(w["intr"].coeffs))
@@ -54,9 +57,33 @@ def compute(name):
             "s_in": int(s["probes_in"]), "greedy_seq": seq.tolist(), "greedy_gain": gain.tolist(), "covered_sha": sha(cov)}
 
 
+def compute_sample(name, w, views):
+    m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
+    it = orc.make_intrinsics(w["intr"].width, w["intr"].height, w["intr"].fx, w["intr"].fy, w["intr"].ppx, w["intr"].ppy, w["intr"].model,
+                             list(w["intr"].coeffs))
+    words = orc.bitset_words(m.n)
+    hit_sha, depth_sha, row_sha, counts = [], [], [], []
+    st = orc.CastStats()
+    for v in views:
+        ok, r, d = m.cast_view_dense(it, w["pose_world"][v], w["init_pos"][v], stats=st)
+        row = orc.bitset_from_ranks(r, words)
+        hit_sha.append(sha(r))
+        depth_sha.append(sha(d))
+        row_sha.append(sha(row))
+        counts.append(int(np.unpackbits(row.view(np.uint8)).sum()))
+    s = st.as_dict()
+    return {"name": name, "n_views": int(w["n_views"]), "views": [int(v) for v in views], "size": [int(w["W"]), int(w["H"])], "full_voxels": int(m.n),
+            "words": int(words), "keys_sha": sha(w["keys"]), "pose_world_sha": sha(w["pose_world"]), "init_pos_sha": sha(w["init_pos"]),
+            "hit_sha": hit_sha, "depth_sha": depth_sha, "row_sha": row_sha, "counts": counts, "rays": int(s["rays"]), "hits": int(s["hits"])}
+
+
 if __name__ == "__main__":
-    out = {"generator": "tests/golden/make_golden_full.py (CPU oracle)", "cases": [compute("C1"), compute("C2")]}
+    # C3: the 1024-view Fibonacci hemisphere at 1280x960 (the strong-scaling workload) -- a sample of its views
+    out = {"generator": "tests/golden/make_golden_full.py (CPU oracle)", "cases": [compute("C1"), compute("C2")],
+           "samples": [compute("C3", [0, 1, 100, 333, 512, 777, 1000, 1023])]}
     with open(os.path.join(HERE, "golden_full.json"), "w") as f:
         json.dump(out, f, indent=1)
     for c in out["cases"]:
         print(c["name"], c["n_views"], "views", c["rays"], "rays", c["hits"], "hits", "S_in", c["s_in"], "greedy", len(c["greedy_seq"]))
+    for c in out["samples"]:
+        print(c["name"], "views", c["views"], c["rays"], "rays", c["hits"], "hits")

@@ -102,3 +102,24 @@ def test_gpu_reproduces_full_size_golden(case, prv, synth, ctx):
     ctx.greedy_async(0, 64)
     seq, gain, cov = ctx.get_greedy(64)
     assert seq.tolist() == case["greedy_seq"] and gain.tolist() == case["greedy_gain"] and sha(cov) == case["covered_sha"]
+
+
+SAMPLES = json.load(open(os.path.join(HERE, "golden", "golden_full.json")))["samples"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", SAMPLES, ids=[c["name"] for c in SAMPLES])
+def test_gpu_reproduces_sampled_views_of_the_1024_view_workload(case, prv, synth, ctx):
+    """C3 (1024 Fibonacci-hemisphere views, 1280x960, the strong-scaling workload): a sample of its views against the oracle."""
+    w = synth.build_workload(prv, case["name"])
+    assert sha(w["keys"]) == case["keys_sha"] and sha(w["pose_world"]) == case["pose_world_sha"] and sha(w["init_pos"]) == case["init_pos_sha"]
+    ids = case["views"]
+    ctx.set_variant(prv.VARIANT_AXIS)
+    ctx.set_map(w["keys"], w["map_rgb"], w["resolution"])
+    ctx.set_camera(w["intr"], 1.0)
+    bits, counts, hit, depth = ctx.cast_views(w["pose_world"][ids], w["init_pos"][ids], mode=prv.MODE_DENSE, want_hit_rank=True, want_depth=True)
+    assert counts.tolist() == case["counts"]
+    for k, v in enumerate(ids):
+        assert sha(hit[k]) == case["hit_sha"][k] and sha(depth[k]) == case["depth_sha"][k] and sha(bits[k]) == case["row_sha"][k], "view %d" % v
+    st = ctx.get_cast_stats()
+    assert st["rays"] == case["rays"] and st["hits"] == case["hits"]

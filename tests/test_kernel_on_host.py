@@ -332,3 +332,9 @@ def test_full_size_golden_views(koh, prv, synth):
             for fine_k, entry in ((0, False), (1, True), (2, True)):
                 hit, depth, st = cast_dense(koh, w, v, 2, fine_k=fine_k, fine_entry=entry)
                 assert sha(hit) == cases[name]["hit_sha"][v] and sha(depth) == cases[name]["depth_sha"][v], (name, v, fine_k, entry)
+    c3 = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_full.json")))["samples"][0]
+    w = synth.build_workload(prv, "C3")
+    for k, v in enumerate(c3["views"][:3]):
+        for fine_k, entry in ((0, False), (1, True)):
+            hit, depth, st = cast_dense(koh, w, v, 2, fine_k=fine_k, fine_entry=entry)
+            assert sha(hit) == c3["hit_sha"][k] and sha(depth) == c3["depth_sha"][k], ("C3", v, fine_k, entry)
