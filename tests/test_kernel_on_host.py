@@ -338,3 +338,30 @@ def test_full_size_golden_views(koh, prv, synth):
         for fine_k, entry in ((0, False), (1, True)):
             hit, depth, st = cast_dense(koh, w, v, 2, fine_k=fine_k, fine_entry=entry)
             assert sha(hit) == c3["hit_sha"][k] and sha(depth) == c3["depth_sha"][k], ("C3", v, fine_k, entry)
+
+
+def test_fast_path_proof_at_its_threshold(koh, prv, orc):
+    """maxRange swept across the exact point where the per-view proof (prv_view_const.hpp) flips: just below the distance to
+    the farthest voxel centre of the AABB grown by one voxel the proof must fail (literal march with the range test), from
+    there on it may hold (range test dropped) -- the results must equal the oracle's either way.  (6 480 more cases run once.)"""
+    rng = np.random.default_rng(77)
+    perms = _signed_permutations()
+    held = failed = 0
+    for case in range(40):
+        w, _ = _random_scene(rng, prv, perms)
+        res = w["resolution"]
+        keys = w["keys"].astype(np.float64)
+        lo = (keys.min(0) - 1 - 32768 + 0.5) * res
+        hi = (keys.max(0) + 1 - 32768 + 0.5) * res
+        pos = (np.floor(w["init_pos"][0] / res) + 0.5) * res  # the snapped origin (main.cpp:112-114)
+        far = float(np.sqrt(sum(max(abs(pos[a] - lo[a]), abs(pos[a] - hi[a])) ** 2 for a in range(3))))
+        for f in (0.999, 0.9999999, 1.0, 1.0000001, 1.001):
+            mr = far * f
+            _, _, o_rank, o_depth, _ = oracle_view(orc, w, 0, max_range=mr)
+            for variant, fine_k, entry in ((1, 0, False), (2, 0, False), (2, 1, True)):
+                hit, depth, st = cast_dense(koh, w, 0, variant, max_range=mr, fine_k=fine_k, fine_entry=entry)
+                assert np.array_equal(hit, o_rank) and np.array_equal(depth, o_depth), (case, f, variant)
+            if st["flags"] & 1 and not st["flags"] & 2:
+                held += 1 if st["flags"] & 4 else 0
+                failed += 0 if st["flags"] & 4 else 1
+    assert held > 30 and failed > 30  # the sweep really straddles the threshold
