@@ -365,3 +365,71 @@ def test_fast_path_proof_at_its_threshold(koh, prv, orc):
                 held += 1 if st["flags"] & 4 else 0
                 failed += 0 if st["flags"] & 4 else 1
     assert held > 30 and failed > 30  # the sweep really straddles the threshold
+
+
+# ---- barrier-free kernels run as kernels on the CPU (tests/cpp/map_kernels_on_host.cpp) ---------------------------------------
+@pytest.fixture(scope="module")
+def mkh(tmp_path_factory):
+    out = tmp_path_factory.mktemp("mkh") / "libmap_kernels_on_host.so"
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-I/usr/local/cuda/include",
+                    "-o", str(out), os.path.join(ROOT, "tests", "cpp", "map_kernels_on_host.cpp")], check=True)
+    return C.CDLL(str(out))
+
+
+def test_map_build_kernels_write_the_documented_tables(mkh, prv, synth):
+    """map_scatter_kernel / map_fine_kernel / map_shell_kernel / map_rank_kernel -- the kernel source, threads executed one
+    after the other -- must leave exactly the occupancy bitmap, shell-padded bitmap, coarse grid, fine grid and rank table that
+    the per-ray checks above run on (built on the host from the documented layout)."""
+    rng = np.random.default_rng(3)
+    perms = _signed_permutations()
+    tables = [synth.build_workload(prv, name, n_views=1, size=(32, 24)) for name in ("C1", "C2")]
+    tables += [_random_scene(rng, prv, perms)[0] for _ in range(40)]
+    for w in tables:
+        keys = np.ascontiguousarray(w["keys"], dtype=np.uint16)
+        for fine_k in (0, 4, 2, 1):
+            rc = mkh.mkh_check_map_kernels(_p(keys, C.c_uint16), C.c_uint32(len(keys)), C.c_double(w["resolution"]), fine_k)
+            assert rc == 0, "table %d differs (%d voxels, fine grid %d)" % (rc, len(keys), fine_k)
+
+
+def test_voxel_mode_kernels_match_oracle(mkh, prv, orc, synth):
+    """project_voxels_kernel, gather_voxel_hits_kernel and precept_points_kernel run as kernels: Perception_3D::precept's
+    cloud->points image against the oracle."""
+    w = synth.build_workload(prv, "C1", n_views=3, size=(320, 240))
+    it = w["intr"]
+    m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
+    ointr = orc.make_intrinsics(it.width, it.height, it.fx, it.fy, it.ppx, it.ppy, it.model, list(it.coeffs))
+    keys = np.ascontiguousarray(w["keys"], dtype=np.uint16)
+    rgb = np.ascontiguousarray(w["map_rgb"], dtype=np.uint8)
+    for v in range(3):
+        ok, o_pts, o_ranks = m.precept(ointr, w["pose_world"][v], w["init_pos"][v])
+        pts = np.zeros(len(keys), dtype=prv.POINT_DTYPE)
+        ranks = np.zeros(len(keys), dtype=np.uint32)
+        pw = np.ascontiguousarray(w["pose_world"][v], dtype=np.float64)
+        ip = np.ascontiguousarray(w["init_pos"][v], dtype=np.float64)
+        rc = mkh.mkh_precept(_p(keys, C.c_uint16), _p(rgb, C.c_uint8), C.c_uint32(len(keys)), C.c_double(w["resolution"]), C.byref(it), C.c_double(1.0),
+                             _p(pw, C.c_double), _p(ip, C.c_double), pts.ctypes.data_as(C.c_void_p), _p(ranks, C.c_uint32))
+        assert rc == 0 and ok
+        assert np.array_equal(ranks, o_ranks)
+        for fld in ("x", "y", "z", "r", "g", "b"):
+            assert np.array_equal(pts[fld], o_pts[fld]), fld
+        assert np.all(pts["w"] == 1.0) and np.all(pts["a"] == 255) and (ranks != orc.NONE).sum() > 100
+
+
+def test_ingest_kernels_match_the_host_map_build(mkh, prv, synth):
+    """prv_set_map_from_cloud's kernels (point -> key, voxel heads, compaction with the first point's colour) run as kernels,
+    cub's stable sort and scan replaced by their definitions: same leaf-ordered keys and colours as prv_host_build_map
+    (main.cpp:1005-1036), including points outside the key range and many points per voxel."""
+    w = synth.build_workload(prv, "C1", n_views=1, size=(32, 24))
+    rng = np.random.default_rng(11)
+    clouds = [(np.ascontiguousarray(w["cloud"], dtype=np.float32), np.ascontiguousarray(w["cloud_rgb"], dtype=np.uint8), w["resolution"])]
+    pts = rng.normal(scale=0.02, size=(20000, 3)).astype(np.float32)       # ~40 points per voxel at 5 mm
+    pts[::97] = 1.0e6                                                        # invalid keys (coordToKeyChecked fails)
+    clouds.append((pts, rng.integers(0, 256, size=(20000, 3)).astype(np.uint8), 0.005))
+    for xyz, rgb, res in clouds:
+        k_ref, c_ref = prv.host_build_map(xyz, rgb, res)
+        keys = np.zeros((len(xyz), 3), dtype=np.uint16)
+        col = np.zeros((len(xyz), 3), dtype=np.uint8)
+        n = mkh.mkh_ingest(_p(xyz, C.c_float), _p(rgb, C.c_uint8), C.c_uint32(len(xyz)), C.c_double(res), _p(keys, C.c_uint16), _p(col, C.c_uint8))
+        assert n == len(k_ref) > 100
+        assert np.array_equal(keys[:n], k_ref) and np.array_equal(col[:n], c_ref)
