@@ -433,3 +433,167 @@ def test_ingest_kernels_match_the_host_map_build(mkh, prv, synth):
         n = mkh.mkh_ingest(_p(xyz, C.c_float), _p(rgb, C.c_uint8), C.c_uint32(len(xyz)), C.c_double(res), _p(keys, C.c_uint16), _p(col, C.c_uint8))
         assert n == len(k_ref) > 100
         assert np.array_equal(keys[:n], k_ref) and np.array_equal(col[:n], c_ref)
+
+
+# ---- the cast KERNELS themselves on a CPU SIMT emulator (tests/cpp/pipeline_on_host.cpp, tests/cpp/simt_on_host.hpp) -------------
+@pytest.fixture(scope="module")
+def poh(tmp_path_factory):
+    out = tmp_path_factory.mktemp("poh") / "libpipeline_on_host.so"
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([gxx, "-O2", "-std=c++20", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-pthread", "-I/usr/local/cuda/include",
+                    "-o", str(out), os.path.join(ROOT, "tests", "cpp", "pipeline_on_host.cpp")], check=True)
+    return C.CDLL(str(out))
+
+
+CONFIGS = ((0, 0), (2, 0), (1, 1))  # (fine cull cell, enter at cell): default pipeline and the two opt-in levels
+
+
+def run_kernels(poh, w, views, mode, fine_k=0, entry=0, grid=2, max_range=1.0, intr=None):
+    """cull -> coarse -> march kernels (and the voxel-mode kernels) as cast_impl launches them, on the emulator."""
+    it = intr if intr is not None else w["intr"]
+    keys = np.ascontiguousarray(w["keys"], dtype=np.uint16)
+    rgb = np.ascontiguousarray(w["map_rgb"], dtype=np.uint8)
+    n, V = len(keys), len(views)
+    words = poh.poh_words(n)
+    gw, gh = (it.width, it.height) if mode == 1 else (it.width + 1, it.height + 1)
+    pw = np.ascontiguousarray(np.asarray(w["pose_world"])[list(views)], dtype=np.float64)
+    ip = np.ascontiguousarray(np.asarray(w["init_pos"])[list(views)], dtype=np.float64)
+    out = dict(bits=np.zeros((V, words), dtype=np.uint64), hit=np.zeros((V, gh, gw), dtype=np.uint32), depth=np.zeros((V, gh, gw), dtype=np.float32),
+               stats=np.zeros((V, 4), dtype=np.uint64), marched=np.zeros(V, dtype=np.uint32), voxel_hit=np.zeros((V, n), dtype=np.uint32))
+    rc = poh.poh_cast_views(_p(keys, C.c_uint16), _p(rgb, C.c_uint8), C.c_uint32(n), C.c_double(w["resolution"]), C.byref(it), C.c_double(max_range),
+                            _p(pw, C.c_double), _p(ip, C.c_double), C.c_uint32(V), mode, fine_k, entry, grid, _p(out["bits"], C.c_uint64),
+                            _p(out["hit"], C.c_uint32), _p(out["depth"], C.c_float), _p(out["stats"], C.c_ulonglong), _p(out["marched"], C.c_uint32),
+                            _p(out["voxel_hit"], C.c_uint32))
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize("name,size,grid", [("C1", (96, 72), 2), ("C2", (64, 48), 3), ("C1", (97, 61), 1)])
+def test_cast_kernels_on_the_emulator_match_oracle(poh, koh, prv, orc, synth, name, size, grid):
+    """cull_kernel, coarse_kernel / coarse_fine_kernel, march_kernel / march_entry_kernel -- kernel source unchanged, one OS
+    thread per CUDA thread -- against the oracle: per-pixel ranks and depths (every pixel written by exactly the kernel that
+    owns it), coverage rows (the atomicOr scatter), per-view counters (the warp-reduced statistics).  Odd image size: the
+    scalar no-hit store path."""
+    w = synth.build_workload(prv, name, n_views=3, size=size)
+    m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
+    words = orc.bitset_words(m.n)
+    for fine_k, entry in CONFIGS:
+        out = run_kernels(poh, w, range(3), 1, fine_k, entry, grid)
+        for v in range(3):
+            _, _, o_rank, o_depth, o_st = oracle_view(orc, w, v)
+            assert np.array_equal(out["hit"][v], o_rank) and np.array_equal(out["depth"][v], o_depth), (name, v, fine_k, entry)
+            assert np.array_equal(out["bits"][v], orc.bitset_from_ranks(o_rank, words))
+            _, _, st = cast_dense(koh, w, v, 2, fine_k=fine_k, fine_entry=bool(entry))  # the per-ray check counts the same work
+            assert out["stats"][v].tolist() == [st["rays"], st["probes"], st["hits"], st["steps"]] and out["marched"][v] == st["marched"]
+            assert st["hits"] == o_st["hits"]
+
+
+def test_cast_kernels_on_the_emulator_full_size_view(poh, prv, synth):
+    """One 640x480 view of the bench workload through the kernels: the region cull inside cull_kernel (whole regions dismissed,
+    128-bit no-hit stores) against the frozen oracle vectors."""
+    import hashlib
+    import json
+    case = [c for c in json.load(open(os.path.join(ROOT, "tests", "golden", "golden_full.json")))["cases"] if c["name"] == "C2"][0]
+    w = synth.build_workload(prv, "C2")
+    v = 37
+    for fine_k, entry in ((0, 0), (1, 1)):
+        out = run_kernels(poh, w, [v], 1, fine_k, entry, grid=4)
+        assert hashlib.sha256(out["hit"][0].tobytes()).hexdigest() == case["hit_sha"][v]
+        assert hashlib.sha256(out["depth"][0].tobytes()).hexdigest() == case["depth_sha"][v]
+        assert hashlib.sha256(out["bits"][0].tobytes()).hexdigest() == case["row_sha"][v]
+        assert out["marched"][0] < 0.15 * 640 * 480
+
+
+def test_voxel_mode_kernels_on_the_emulator(poh, prv, orc, synth):
+    """Voxel-driven mode end to end as kernels: project_voxels_kernel -> cull_kernel<MASKED> -> coarse -> march ->
+    gather_voxel_hits_kernel, against Perception_3D::precept of the oracle."""
+    w = synth.build_workload(prv, "C1", n_views=2, size=(160, 120))
+    it = w["intr"]
+    m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
+    ointr = orc.make_intrinsics(it.width, it.height, it.fx, it.fy, it.ppx, it.ppy, it.model, list(it.coeffs))
+    words = orc.bitset_words(m.n)
+    for fine_k, entry in ((0, 0), (1, 1)):
+        out = run_kernels(poh, w, range(2), 0, fine_k, entry)
+        for v in range(2):
+            ok, _, o_ranks = m.precept(ointr, w["pose_world"][v], w["init_pos"][v])
+            assert ok and np.array_equal(out["voxel_hit"][v], o_ranks), (v, fine_k, entry)
+            assert np.array_equal(out["bits"][v], orc.bitset_from_ranks(o_ranks, words))
+            assert (o_ranks != orc.NONE).sum() > 100
+
+
+def test_special_views_on_the_emulator(poh, prv, orc, synth):
+    """Camera inside an occupied voxel, camera outside the key range, and maxRange inside the scene (views without the
+    fast-path proof go through the same queues but are marched literally) in one launch with an ordinary view."""
+    w = synth.build_workload(prv, "C1", n_views=4, size=(64, 48))
+    res = w["resolution"]
+    k = w["keys"][len(w["keys"]) // 2].astype(np.float64)
+    w["init_pos"][1] = (k - 32768 + 0.5) * res           # "view in the object" (main.cpp:263-267)
+    w["init_pos"][2] = np.array([1.0e6, 0.0, 0.0])       # "View out of map" (main.cpp:139)
+    for max_range in (1.0, 0.3):
+        for fine_k, entry in ((0, 0), (1, 1)):
+            out = run_kernels(poh, w, range(4), 1, fine_k, entry, max_range=max_range)
+            for v in range(4):
+                _, _, o_rank, o_depth, _ = oracle_view(orc, w, v, max_range=max_range)
+                if v in (1, 2):  # such views launch no rays; cull_kernel still records "no hit" for every pixel
+                    assert np.all(o_rank == 0xFFFFFFFF) and int(out["stats"][v][0]) == 0 and not out["bits"][v].any()
+                assert np.array_equal(out["hit"][v], o_rank) and np.array_equal(out["depth"][v], o_depth), (v, max_range, fine_k, entry)
+
+
+def test_splat_kernels_on_the_emulator(poh, prv, orc, synth):
+    """splat_points_kernel (64-bit atomicMin on the corner cell) + splat_resolve_kernel (shared-memory tile) as kernels:
+    RGBA bit-exact and depth identical to the oracle's frozen splat definition (north-star tolerance: 1e-5 relative)."""
+    w = synth.build_workload(prv, "C1", n_views=3, size=(96, 72))
+    it = w["intr"]
+    ointr = orc.make_intrinsics(it.width, it.height, it.fx, it.fy, it.ppx, it.ppy, it.model, list(it.coeffs))
+    xyz = np.ascontiguousarray(w["cloud"][::3], dtype=np.float32)  # a third of the points: one OS thread per point and view
+    rgb = np.ascontiguousarray(w["cloud_rgb"][::3], dtype=np.uint8)
+    pw = np.ascontiguousarray(w["pose_world"], dtype=np.float64)
+    for point_size in (5, 2):
+        rgba = np.zeros((3, it.height, it.width, 4), dtype=np.uint8)
+        depth = np.zeros((3, it.height, it.width), dtype=np.float32)
+        rc = poh.poh_render_views(_p(xyz, C.c_float), _p(rgb, C.c_uint8), C.c_uint64(len(xyz)), C.byref(it), _p(pw, C.c_double), C.c_uint32(3), point_size,
+                                  _p(rgba, C.c_uint8), _p(depth, C.c_float))
+        assert rc == 0
+        for v in range(3):
+            o_rgba, o_depth, _ = orc.splat(xyz, rgb, ointr, w["pose_world"][v], point_size)
+            assert np.array_equal(rgba[v], o_rgba), (v, point_size)
+            np.testing.assert_allclose(depth[v], o_depth, rtol=1e-5, atol=0)
+            assert np.array_equal(depth[v], o_depth) and (o_rgba[..., 3] > 0).sum() > 50
+
+
+@pytest.mark.parametrize("method,E", [(3, 5), (3, 2), (2, 2)])
+def test_ensemble_kernels_on_the_emulator(poh, orc, method, E):
+    """ensemble_terms_kernel + ensemble_sum_kernel (nbv_loop cases 2 / 3, main.cpp:2039-2161) as kernels: bit-exact scores for
+    method 3 and for method 2 at the reference's ensemble of two."""
+    rng = np.random.default_rng(9)
+    V, H, W = 7, 45, 80
+    images = rng.integers(0, 256, size=(V, E, H, W, 4)).astype(np.uint8)
+    images[2, :, :10] = images[2, 0:1, :10]  # zero-variance pixels (method 2 skips them)
+    scores = np.zeros(V)
+    rc = poh.poh_score_ensemble(_p(images, C.c_uint8), C.c_uint32(V), C.c_uint32(E), W, H, method, _p(scores, C.c_double))
+    assert rc == 0
+    _, o_scores = orc.score_ensemble(images, method)
+    assert np.array_equal(scores, o_scores)
+
+
+def test_kernels_are_race_free_under_threadsanitizer(tmp_path):
+    """The emulator runs CUDA threads as real concurrent OS threads synchronised only by the kernels' own barriers, warp
+    collectives and atomics -- so ThreadSanitizer sees what compute-sanitizer's racecheck sees on the device, and more (global
+    memory too).  The cull / coarse / march / voxel-mode / splat kernels must run without a single report; the one suppressed
+    site is write_hit's deliberate test-before-atomicOr (tests/tsan/suppressions.txt)."""
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    tsan = subprocess.run([gxx, "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(tsan) or not os.path.exists(tsan):
+        pytest.skip("libtsan not installed")
+    lib = tmp_path / "libpipeline_on_host_tsan.so"
+    subprocess.run([gxx, "-O1", "-g", "-std=c++20", "-ffp-contract=off", "-fsanitize=thread", "-shared", "-fPIC", "-pthread", "-I/usr/local/cuda/include",
+                    "-o", str(lib), os.path.join(ROOT, "tests", "cpp", "pipeline_on_host.cpp")], check=True)
+    env = dict(os.environ, LD_PRELOAD=tsan,
+               TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 history_size=2 suppressions=" + os.path.join(ROOT, "tests", "tsan", "suppressions.txt"))
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tsan", "run_kernels_under_tsan.py"), str(lib)], env=env, capture_output=True, text=True,
+                       timeout=600)
+    if "KERNELS-RAN-UNDER-TSAN" not in r.stdout and "ThreadSanitizer" not in r.stderr:
+        pytest.skip("the interpreter does not run under libtsan here: " + r.stderr[-300:])
+    assert "KERNELS-RAN-UNDER-TSAN" in r.stdout, r.stderr[-2000:]
+    assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[:4000]
