@@ -59,6 +59,9 @@ __global__ void __launch_bounds__(256) greedy_iter_kernel(const uint64_t* rows, 
     if (threadIdx.x == 0) atomicMax(best + k, ((unsigned long long)t << 32) | (unsigned long long)(0xFFFFFFFFu - view_ids[blockIdx.x]));
 }
 
+// (The two kernels below need cooperative grid sync / thread-block clusters with PTX: not part of the CPU emulation of
+// tests/cpp/pipeline_on_host.cpp, which defines PRVK_HOST_CHECK and runs the kernels above.)
+#ifndef PRVK_HOST_CHECK
 // Whole greedy loop in ONE persistent kernel (cooperative launch: every block is resident).  Each block keeps the
 // covered mask in shared memory and scores its rows (row r -> block r mod gridDim) against it; the per-iteration argmax
 // is one 64-bit atomicMax per block followed by a grid barrier (cooperative_groups grid sync); every block
@@ -389,3 +392,4 @@ __global__ void __launch_bounds__(kGreedyClusterThreads) greedy_cluster_kernel(c
     for (uint32_t w = threadIdx.x; w < slice; w += blockDim.x)
         if (w_lo + w < half) reinterpret_cast<ulonglong2*>(cov_out)[w_lo + w] = cov[w];
 }
+#endif  // PRVK_HOST_CHECK

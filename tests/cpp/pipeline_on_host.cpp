@@ -29,6 +29,9 @@ static inline float __uint_as_float(uint32_t u) {
 }
 #include "../../nerf-prv_b200/csrc/kernels_ensemble.cuh"
 #include "../../nerf-prv_b200/csrc/kernels_splat.cuh"
+#undef __shared__
+#define __shared__ static
+#include "../../nerf-prv_b200/csrc/kernels_greedy.cuh"  // popcount_rows_kernel, greedy_init_kernel, greedy_iter_kernel (PRVK_HOST_CHECK hides the rest)
 
 extern "C" {
 
@@ -56,6 +59,39 @@ int poh_render_views(const float* xyz, const uint8_t* rgb, uint64_t P, const prv
     simt_launch(dim3((W + 31) / 32, (H + 7) / 8, V), dim3(256),
                 [&] { splat_resolve_kernel(corner.data(), Wc, Hc, W, H, point_size, rgb, rgba_out, depth_out, 0u); });
     return 0;
+}
+
+// popcount_rows_kernel (coverage counts, always on the path) and the one-launch-per-iteration greedy of greedy_impl
+// (greedy_init_kernel + greedy_iter_kernel: the path for coverage masks too large for the cluster / grid-barrier kernels).
+// rows [V][words] u64, ids[V] = global view ids.  seq / gains need room for max_iter + 1 entries; returns their number.
+int poh_counts_and_greedy(const uint64_t* rows, uint32_t V, uint32_t words, const uint32_t* ids, uint32_t first_view, uint32_t max_iter,
+                          uint32_t* counts_out, uint32_t* seq_out, uint32_t* gains_out, uint64_t* covered_out) {
+    if (!rows || !ids || !counts_out || !seq_out || !gains_out || V == 0 || (words & 1u)) return -1;
+    simt_launch(dim3(V), dim3(256), [&] { popcount_rows_kernel(rows, words, counts_out); });
+    uint32_t max_id = 0;
+    for (uint32_t v = 0; v < V; v++) max_id = std::max(max_id, ids[v]);
+    std::vector<uint32_t> row_of_id((size_t)max_id + 1, kNone);
+    for (uint32_t v = 0; v < V; v++) row_of_id[ids[v]] = v;
+    if (first_view > max_id || row_of_id[first_view] == kNone) return -1;
+    std::vector<unsigned long long> best((size_t)max_iter + 2, 0ull);
+    std::vector<uint64_t> cov[2] = {std::vector<uint64_t>(words, 0), std::vector<uint64_t>(words, 0)};
+    simt_launch(dim3(1), dim3(256), [&] { greedy_init_kernel(rows, words, row_of_id[first_view], first_view, best.data()); });
+    for (uint32_t k = 1; k <= max_iter + 1; k++) {
+        const int cover_only = k == max_iter + 1;
+        simt_launch(dim3(cover_only ? 1 : V), dim3(256), [&] {
+            greedy_iter_kernel(rows, words, ids, row_of_id.data(), k, best.data(), cov[(k - 1) & 1].data(), cov[k & 1].data(), cover_only);
+        });
+    }
+    uint32_t n = 0;  // prv_get_greedy
+    for (uint32_t k = 0; k <= max_iter; k++) {
+        const uint32_t g = (uint32_t)(best[k] >> 32);
+        if (k > 0 && g == 0) break;
+        seq_out[n] = 0xFFFFFFFFu - (uint32_t)(best[k] & 0xFFFFFFFFull);
+        gains_out[n] = g;
+        n++;
+    }
+    if (covered_out) std::memcpy(covered_out, cov[n & 1].data(), (size_t)words * 8);
+    return (int)n;
 }
 
 // prv_score_ensemble's two kernels (method 2 with E == 2 uses the host-libm table of logs, as the library does)

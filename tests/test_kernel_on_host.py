@@ -597,3 +597,33 @@ def test_kernels_are_race_free_under_threadsanitizer(tmp_path):
         pytest.skip("the interpreter does not run under libtsan here: " + r.stderr[-300:])
     assert "KERNELS-RAN-UNDER-TSAN" in r.stdout, r.stderr[-2000:]
     assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[:4000]
+
+
+def test_count_and_iterative_greedy_kernels_on_the_emulator(poh, orc):
+    """popcount_rows_kernel and the launch-per-iteration greedy (greedy_init_kernel / greedy_iter_kernel, 64-bit atomicMax of
+    (gain << 32 | ~view id)) as kernels against the oracle's greedy: ties go to the lowest view id, empty and duplicate rows,
+    permuted global view ids, early stop at gain 0 and the max_iter cut."""
+    rng = np.random.default_rng(21)
+    for trial in range(4):
+        V, words = int(rng.integers(3, 24)), 2 * int(rng.integers(1, 4))
+        rows = rng.integers(0, 2 ** 63, size=(V, words), dtype=np.uint64) & rng.integers(0, 2 ** 63, size=(V, words), dtype=np.uint64)
+        if trial % 2 == 0:
+            rows &= rng.integers(0, 2 ** 63, size=(V, words), dtype=np.uint64)  # sparser: more ties
+        rows[V // 2] = 0                      # an empty row
+        rows[V - 1] = rows[0]                 # a duplicate: tie on every gain
+        ids = np.arange(V, dtype=np.uint32) if trial < 2 else rng.permutation(V).astype(np.uint32)
+        max_iter = 24 if trial != 1 else 3
+        first = int(ids[int(rng.integers(0, V))])
+        counts = np.zeros(V, dtype=np.uint32)
+        seq = np.zeros(max_iter + 1, dtype=np.uint32)
+        gains = np.zeros(max_iter + 1, dtype=np.uint32)
+        cov = np.zeros(words, dtype=np.uint64)
+        n = poh.poh_counts_and_greedy(_p(rows, C.c_uint64), C.c_uint32(V), C.c_uint32(words), _p(ids, C.c_uint32), C.c_uint32(first), C.c_uint32(max_iter),
+                                      _p(counts, C.c_uint32), _p(seq, C.c_uint32), _p(gains, C.c_uint32), _p(cov, C.c_uint64))
+        assert n > 0
+        assert counts.tolist() == [int(np.unpackbits(r.view(np.uint8)).sum()) for r in rows]
+        # oracle greedy works on rows indexed by view id
+        order = np.argsort(ids, kind="stable")
+        o_seq, o_gain, o_cov, _ = orc.greedy(rows[order], first, max_iter)
+        assert seq[:n].tolist() == o_seq.tolist() and gains[:n].tolist() == o_gain.tolist(), trial
+        assert np.array_equal(cov, o_cov)
