@@ -437,3 +437,24 @@ def score_ensemble(images, method, chosen=None):
     ch = None if chosen is None else np.ascontiguousarray(chosen, dtype=np.uint8)
     best = lib().orc_score_ensemble(_ptr(im, C.c_uint8), V, E, W, H, method, None if ch is None else _ptr(ch, C.c_uint8), _ptr(scores, C.c_double))
     return best, scores
+
+
+class HostShim:
+    """The names nerf_prv_b200/synth.py::build_workload needs from a host provider (normalisation, map insertion, view
+    space, poses), answered by the oracle's own restatements instead of the product's host shim.  The reference arm of
+    bench.py and the golden generators build their workloads through this, so neither needs libprv_b200.so."""
+    make_intrinsics = staticmethod(make_intrinsics)
+    host_normalize_cloud = staticmethod(normalize_cloud)
+    host_view_space = staticmethod(view_space)
+
+    @staticmethod
+    def host_build_map(points, rgb, resolution):
+        m = Map.from_points(points, rgb, resolution)
+        return m.keys.copy(), m.rgb.copy()
+
+    @staticmethod
+    def view_poses(init_pos, object_center):
+        out = np.zeros((len(init_pos), 4, 4))
+        for v, ip in enumerate(init_pos):
+            out[v] = view_pose_world(view_pose(ip, object_center))
+        return out
