@@ -167,7 +167,7 @@ def _config(w, args, world):
                         % (args.workload, w["name"], len(w["cloud"]), len(w["keys"]), w["resolution"], w["n_views"], w["W"], w["H"], GREEDY_MAX_ITER),
             "objects_per_step": world if args.workload != "C3" else 1, "views": w["n_views"], "width": w["W"], "height": w["H"],
             "voxels": int(len(w["keys"])), "resolution_m": w["resolution"], "l2": "flushed between timed steps (256 MiB memset, untimed)",
-            "variant": args.variant, "fine_cull": getattr(args, "fine_cull", 0), "fine_entry": bool(getattr(args, "fine_entry", False))}
+            "variant": args.variant, "brick": getattr(args, "brick", 8), "brick_entry": bool(getattr(args, "brick_entry", 1))}
 
 
 def run_own(args):
@@ -188,8 +188,7 @@ def run_own(args):
     w = synth.build_workload(prv, args.workload, obj_index=obj_index)
     ctx = prv.Context(local)
     ctx.set_variant(args.variant)
-    if args.fine_cull:
-        ctx.set_fine_cull(args.fine_cull, args.fine_entry)  # opt-in second level of the brick cull (same results; see include/prv.h)
+    ctx.set_brick_cull(args.brick, bool(args.brick_entry))  # tuning only: results are identical for every setting (include/prv.h)
     ctx.set_map(w["keys"], w["map_rgb"], w["resolution"])
     ctx.set_camera(w["intr"], 1.0)
     V = w["n_views"]
@@ -409,8 +408,8 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--variant", type=int, default=2)
-    ap.add_argument("--fine-cull", type=int, default=0, choices=[0, 1, 2, 4], help="prv_set_fine_cull cell size in voxels (0 = off, the default path)")
-    ap.add_argument("--fine-entry", action="store_true", help="with --fine-cull: start the exact march at the first set fine cell")
+    ap.add_argument("--brick", type=int, default=8, choices=[4, 8, 16], help="prv_set_brick_cull: brick edge of the conservative cull in voxels")
+    ap.add_argument("--brick-entry", type=int, default=1, choices=[0, 1], help="prv_set_brick_cull: start the exact march at the first set brick")
     ap.add_argument("--cpu-views", type=int, default=16, help="views in the cpu_baseline sample (~10-30 s of CPU work across the host cores)")
     ap.add_argument("--ref-views", type=int, default=2, help="views per step of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -111,14 +111,13 @@ const char* prv_last_error(const prv_ctx* ctx); /* ctx may be NULL: last create 
 int         prv_device_info(prv_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, uint64_t* mem_bytes);
 int         prv_sync(prv_ctx* ctx);
 int         prv_set_variant(prv_ctx* ctx, int variant);
-/* Optional second level of the conservative brick cull in front of the exact march (variant AXIS): a finer occupancy grid
- * (cells of `cell` = 1, 2 or 4 voxels, dilated by one voxel like the 8-voxel bricks) that proves more through-the-AABB
- * misses without marching them.  With enter_at_cell != 0 the exact march of a surviving ray additionally starts where the
- * ray enters the first set fine cell (grown by one voxel) instead of at the AABB face: the voxels in between are provably
- * empty and are crossed by the cheap per-axis additions.  Results are identical with and without either; they only move
- * work between kernels (the probes_in / marched counters of prv_cast_stats change accordingly).
- * cell = 0: off (default).  Takes effect at the next prv_set_map / prv_set_map_from_cloud. */
-int         prv_set_fine_cull(prv_ctx* ctx, int cell, int enter_at_cell);
+/* Tuning of the conservative brick cull in front of the exact march (variant AXIS).  `cell` = edge of the bricks of the
+ * coarse occupancy grid in voxels (4, 8 or 16; default 8).  With enter_at_brick != 0 (default) the exact march of a
+ * surviving ray starts where the ray enters the first set brick of the cull's walk (grown by one voxel) instead of at the
+ * AABB face: the voxels in between are provably empty and are crossed by the cheap per-axis additions.  Results are
+ * identical for every setting; only the probes_in / marched counters of prv_cast_stats move.
+ * Takes effect at the next prv_set_map / prv_set_map_from_cloud. */
+int         prv_set_brick_cull(prv_ctx* ctx, int cell, int enter_at_brick);
 
 /* ---------------------------------------------------------------- host-side logic (pure host, no device)
  * One implementation of the reference's pose / view-space / map-insertion arithmetic for every caller. */

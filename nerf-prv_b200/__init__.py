@@ -88,7 +88,7 @@ def lib():
         "prv_device_info": (i, [vp, P(i), P(i), P(i), P(u64)]),
         "prv_sync": (i, [vp]),
         "prv_set_variant": (i, [vp, i]),
-        "prv_set_fine_cull": (i, [vp, i, i]),
+        "prv_set_brick_cull": (i, [vp, i, i]),
         "prv_host_mat4_inverse": (i, [P(d), P(d)]),
         "prv_host_view_pose": (i, [P(d), P(d), P(d), P(d)]),
         "prv_host_view_pose_world": (i, [P(d), P(d), P(d)]),
@@ -296,10 +296,10 @@ class Context:
     def set_variant(self, v):
         self._chk(lib().prv_set_variant(self._h, v))
 
-    def set_fine_cull(self, cell, enter_at_cell=False):
-        """Second level of the brick cull (0 = off, default; 1, 2 or 4 voxels); enter_at_cell: start the exact march at the
-        first set fine cell.  Applies to the next set_map."""
-        self._chk(lib().prv_set_fine_cull(self._h, cell, 1 if enter_at_cell else 0))
+    def set_brick_cull(self, cell=8, enter_at_brick=True):
+        """Brick edge of the conservative cull (4, 8 or 16 voxels) and whether the exact march starts at the first set
+        brick.  Applies to the next set_map; results are identical for every setting."""
+        self._chk(lib().prv_set_brick_cull(self._h, cell, 1 if enter_at_brick else 0))
 
     def set_map(self, keys, rgb, resolution):
         k = np.ascontiguousarray(keys, dtype=np.uint16)

@@ -89,7 +89,7 @@ __device__ __forceinline__ void block_append(bool keep, uint32_t value, uint32_t
     __syncthreads();  // s_woff / s_base are reused by the next chunk
 }
 
-// same, two parallel queues (pixel, fine cell)
+// same, two parallel queues (pixel, entry brick)
 __device__ __forceinline__ void block_append2(bool keep, uint32_t v1, uint32_t v2, uint32_t* q1, uint32_t* q2, uint32_t* count_view, uint32_t* s_woff,
                                               uint32_t* s_base) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -273,8 +273,8 @@ __device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint3
     __syncthreads();
 }
 
-template <bool FINE>
-__device__ __forceinline__ void coarse_body(const CastParams& p) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
     __shared__ ViewConst s_vc;
     __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
     __shared__ uint32_t s_woff[8];
@@ -318,7 +318,7 @@ __device__ __forceinline__ void coarse_body(const CastParams& p) {
             } else {
                 float dx, dy, dz;
                 ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
-                keep = FINE ? !coarse_miss_fine(p.map, vc, dx, dy, dz, cell) : !coarse_miss(p.map, vc, dx, dy, dz);
+                keep = !coarse_miss(p.map, vc, dx, dy, dz, cell);
             }
             if (!keep && p.pix_hit) {
                 const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
@@ -326,15 +326,12 @@ __device__ __forceinline__ void coarse_body(const CastParams& p) {
                 if (p.pix_depth) p.pix_depth[o] = 0.0f;
             }
         }
-        if (FINE && p.queue2b)
+        if (p.queue2b)
             block_append2(keep, pid, cell, p.queue2 + (size_t)view * p.queue_cap, p.queue2b + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
         else
             block_append(keep, pid, p.queue2 + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
     }
 }
-__global__ void __launch_bounds__(256, 8) coarse_kernel(const CastParams p) { coarse_body<false>(p); }
-// with the optional second cull level (prv_set_fine_cull): the nested walk needs ~50 registers, so 4 blocks/SM
-__global__ void __launch_bounds__(256, 4) coarse_fine_kernel(const CastParams p) { coarse_body<true>(p); }
 
 // Persistent WARPS: every warp pulls 32-ray chunks of the flattened (view, chunk) list with its own atomic ticket and
 // shares nothing with the other warps of its block after the chunk-prefix table is built -- no block barrier in the loop
@@ -343,8 +340,8 @@ __global__ void __launch_bounds__(256, 4) coarse_fine_kernel(const CastParams p)
 // hidden (un-prefetched warp tickets had measured 6 % slower than block tickets).  Measured on C2: 56 registers / 32 warps
 // per SM (no spills) 0.514 ms, 48 / 40 (16 B spilled) 0.521 ms, 40 / 48 (88 B spilled) 0.530 ms.
 constexpr int kMarchBlock = 256, kMarchMinBlocks = 4;
-template <int BS, int MINB, bool ENTRY>
-__device__ __forceinline__ void march_body(const CastParams& p) {
+template <int BS, int MINB>
+__global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
     __shared__ ViewConst s_vcw[BS / 32];
     __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
     build_chunk_prefix(p.qcount2 + p.view_base, p.nviews, s_prefix, 32u);
@@ -378,7 +375,7 @@ __device__ __forceinline__ void march_body(const CastParams& p) {
         const uint32_t idx = (g - s_prefix[vl]) * 32u + (uint32_t)lane;
         if (idx < count) {
             const uint32_t packed = p.queue2[(size_t)view * p.queue_cap + idx];
-            const uint32_t cell = ENTRY ? p.queue2b[(size_t)view * p.queue_cap + idx] : kNone;
+            uint32_t cell = p.queue2b ? p.queue2b[(size_t)view * p.queue_cap + idx] : kNone;  // brick entry (prv_set_brick_cull)
             const int py = (int)(packed >> 16), px = (int)(packed & 0xFFFFu);
             const uint32_t pid = (uint32_t)py * (uint32_t)p.GW + (uint32_t)px;
             CastResult res;
@@ -386,14 +383,18 @@ __device__ __forceinline__ void march_body(const CastParams& p) {
             res.steps = 0;
             res.probes = 0;
             res.k0 = res.k1 = res.k2 = 0;
-            RayState r;
-            float dx, dy, dz;
-            ray_direction(p.cam, vc, px, py, dx, dy, dz);
-            if (ray_init(vc, p.map.resolution, dx, dy, dz, r)) {
-                if (!(vc.flags & kViewFastOk))
+#pragma unroll 1
+            for (;;) {  // a second pass only when a brick box could not be entered (never observed): start over from the AABB face
+                RayState r;
+                float dx, dy, dz;
+                ray_direction(p.cam, vc, px, py, dx, dy, dz);
+                if (!ray_init(vc, p.map.resolution, dx, dy, dz, r)) break;
+                if (!(vc.flags & kViewFastOk)) {
                     march_plain(p.map, p.cam, vc, r, res);
-                else if (!ENTRY || cell == kNone || !march_axis_box(p.map, vc, r, cell, res))
-                    march_axis(p.map, vc, r, res);
+                    break;
+                }
+                if (march_axis(p.map, vc, r, cell, res)) break;
+                cell = kNone;
             }
             write_hit(p, vc, view, pid, res);
             c_probes += res.probes;
@@ -404,11 +405,6 @@ __device__ __forceinline__ void march_body(const CastParams& p) {
     }
     if (cur_view != 0xFFFFFFFFu) warp_commit_stats(p.stats + 4 * (size_t)cur_view, c_probes, c_hits, c_steps);
 }
-template <int BS, int MINB>
-__global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) { march_body<BS, MINB, false>(p); }
-// optional: the exact march starts at the fine cell found by coarse_fine_kernel (prv_set_fine_cull(cell, 1))
-template <int BS, int MINB>
-__global__ void __launch_bounds__(BS, MINB) march_entry_kernel(const CastParams p) { march_body<BS, MINB, true>(p); }
 
 // ---- PLAIN / FAST variants: one kernel, one thread per pixel of a 32x8 tile ----------------------------------------
 template <int VARIANT, bool MASKED>

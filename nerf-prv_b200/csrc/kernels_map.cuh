@@ -13,8 +13,7 @@ struct MapBuild {
     uint32_t* prefix;
     uint32_t* leaf_of_raster;
     const uint16_t* keys;
-    uint32_t* fine;  // optional second cull level (fine_k > 0): cells of fine_k voxels
-    int nf[3], fine_k;
+    int cs;  // brick edge in voxels
 };
 
 // per occupied voxel: occupancy bit, padded-bitmap bit, and the (<= 8) coarse cells within one voxel of it
@@ -28,8 +27,8 @@ __global__ void __launch_bounds__(256) map_scatter_kernel(MapBuild b) {
     const int q[3] = {q0, q1, q2};
     int cl[3], ch[3];
     for (int a = 0; a < 3; a++) {
-        cl[a] = max(0, (q[a] - 1) / kCoarse);
-        ch[a] = min(b.nc[a] - 1, (q[a] + 1) / kCoarse);
+        cl[a] = max(0, (q[a] - 1) / b.cs);
+        ch[a] = min(b.nc[a] - 1, (q[a] + 1) / b.cs);
     }
     for (int K = cl[2]; K <= ch[2]; K++)
         for (int J = cl[1]; J <= ch[1]; J++)
@@ -39,25 +38,6 @@ __global__ void __launch_bounds__(256) map_scatter_kernel(MapBuild b) {
                 const uint32_t c = (uint32_t)((K * b.nc[1] + J) * b.nc[0] + I);
                 const uint32_t bit = 1u << (c & 31);
                 if (!(__ldcg(b.coarse + (c >> 5)) & bit)) atomicOr(b.coarse + (c >> 5), bit);
-            }
-}
-
-// optional fine cull grid: per occupied voxel, the (<= 27) cells of fine_k voxels within one voxel of it
-__global__ void __launch_bounds__(256) map_fine_kernel(MapBuild b) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= b.n_occ) return;
-    const int q[3] = {b.keys[3 * i] - b.lo[0], b.keys[3 * i + 1] - b.lo[1], b.keys[3 * i + 2] - b.lo[2]};
-    int cl[3], ch[3];
-    for (int a = 0; a < 3; a++) {
-        cl[a] = max(0, q[a] - 1) / b.fine_k;
-        ch[a] = min(b.n[a] - 1, q[a] + 1) / b.fine_k;
-    }
-    for (int K = cl[2]; K <= ch[2]; K++)
-        for (int J = cl[1]; J <= ch[1]; J++)
-            for (int I = cl[0]; I <= ch[0]; I++) {
-                const uint32_t c = (uint32_t)((K * b.nf[1] + J) * b.nf[0] + I);
-                const uint32_t bit = 1u << (c & 31);
-                if (!(__ldcg(b.fine + (c >> 5)) & bit)) atomicOr(b.fine + (c >> 5), bit);
             }
 }
 

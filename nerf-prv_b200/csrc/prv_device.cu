@@ -74,7 +74,7 @@ struct prv_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     int variant = PRV_VARIANT_AXIS;
-    int occ_coarse = 0, occ_coarse_fine = 0, occ_march = 0, occ_march_entry = 0, occ_greedy = 0;
+    int occ_coarse = 0, occ_march = 0, occ_greedy = 0, coarse_minb = 8;
     uint32_t occ_greedy_words = 0;
     bool greedy_persistent = false;
     // PRV_GREEDY_CLUSTER=0 forces the grid-barrier kernel (the fallback for tables larger than one cluster's shared memory)
@@ -91,9 +91,8 @@ struct prv_ctx {
     double resolution = 0;
     int lo[3] = {0, 0, 0}, n[3] = {0, 0, 0};
     DevBuf d_coarse;
-    DevBuf d_fine;   // optional second cull level (prv_set_fine_cull)
-    int fine_k = 0;  // cell size requested for the NEXT prv_set_map; ctx->map.fine_k is what the resident map carries
-    bool fine_entry = false;  // start the exact march at the fine cell that stopped the nested walk (needs fine_k > 0)
+    int brick_cs = kCoarseDefault;  // brick edge requested for the NEXT prv_set_map; ctx->map.cs is what the resident map carries
+    bool brick_entry = true;        // start the exact march at the first set brick of the coarse walk (prv_set_brick_cull)
     DevBuf d_bitmap, d_bitmap_pad, d_prefix, d_leaf_of_raster, d_keys, d_rgb, d_tilesum;
     std::vector<uint16_t> h_keys;
 
@@ -401,9 +400,7 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
         p.queue2 = ptr<uint32_t>(ctx->d_queue2);
         p.qcount2 = ptr<uint32_t>(ctx->d_qcount) + V;
         p.queue_cap = ctx->pix_stride;
-        // fine-cell entry needs the packed cell coordinates to fit (kFineCellBits per axis)
-        const bool entry = ctx->fine_entry && ctx->map.fine_k > 0 && std::max(ctx->map.nf[0], std::max(ctx->map.nf[1], ctx->map.nf[2])) <= (1 << kFineCellBits);
-        if (entry) {
+        if (ctx->brick_entry) {  // (a grid too large to pack its brick coordinates reports no brick: coarse_miss)
             if ((rc = ensure(ctx, ctx->d_queue2b, (size_t)V * ctx->pix_stride * 4))) return rc;
             p.queue2b = ptr<uint32_t>(ctx->d_queue2b);
         }
@@ -423,13 +420,13 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
         if (ctx->variant == PRV_VARIANT_AXIS) {
             p.tickets = ptr<uint32_t>(ctx->d_tickets) + 2 * li;
             if (ctx->occ_coarse == 0) {  // persistent grids = exactly one resident wave
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_coarse, coarse_kernel, 256, 0);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_coarse_fine, coarse_fine_kernel, 256, 0);
+                ctx->coarse_minb = getenv("PRV_COARSE_MINB") ? atoi(getenv("PRV_COARSE_MINB")) : 8;  // (experiment switch; 8 or 6)
+                if (ctx->coarse_minb == 6)
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_coarse, coarse_kernel<6>, 256, 0);
+                else
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_coarse, coarse_kernel<8>, 256, 0);
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march, march_kernel<kMarchBlock, kMarchMinBlocks>, kMarchBlock, 0);
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march_entry, march_entry_kernel<kMarchBlock, kMarchMinBlocks>, kMarchBlock, 0);
-                ctx->occ_march_entry = std::max(1, ctx->occ_march_entry);
                 ctx->occ_coarse = std::max(1, ctx->occ_coarse);
-                ctx->occ_coarse_fine = std::max(1, ctx->occ_coarse_fine);
                 ctx->occ_march = std::max(1, ctx->occ_march);
             }
             {
@@ -439,16 +436,13 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels) {
                     cull_kernel<true><<<rgrid, 256, 0, ctx->stream>>>(p);
                 else
                     cull_kernel<false><<<rgrid, 256, 0, ctx->stream>>>(p);
-                if (p.map.fine_k > 0)
-                    coarse_fine_kernel<<<(uint32_t)(ctx->sm_count * ctx->occ_coarse_fine), 256, 0, ctx->stream>>>(p);
+                if (ctx->coarse_minb == 6)
+                    coarse_kernel<6><<<(uint32_t)(ctx->sm_count * ctx->occ_coarse), 256, 0, ctx->stream>>>(p);
                 else
-                    coarse_kernel<<<(uint32_t)(ctx->sm_count * ctx->occ_coarse), 256, 0, ctx->stream>>>(p);
+                    coarse_kernel<8><<<(uint32_t)(ctx->sm_count * ctx->occ_coarse), 256, 0, ctx->stream>>>(p);
             }
             Span s(ctx, K_MARCH, 1);
-            if (p.queue2b)
-                march_entry_kernel<kMarchBlock, kMarchMinBlocks><<<(uint32_t)(ctx->sm_count * ctx->occ_march_entry), kMarchBlock, 0, ctx->stream>>>(p);
-            else
-                march_kernel<kMarchBlock, kMarchMinBlocks><<<(uint32_t)(ctx->sm_count * ctx->occ_march), kMarchBlock, 0, ctx->stream>>>(p);
+            march_kernel<kMarchBlock, kMarchMinBlocks><<<(uint32_t)(ctx->sm_count * ctx->occ_march), kMarchBlock, 0, ctx->stream>>>(p);
         } else {
             Span s(ctx, K_CAST, 1);
             if (ctx->variant == PRV_VARIANT_PLAIN)
@@ -663,13 +657,6 @@ int prv_create(prv_ctx** out, int device) {
     for (auto& s : ctx->slots) cudaEventCreate(&s);
     cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
     if (const char* e = getenv("PRV_GREEDY_CLUSTER")) ctx->greedy_no_cluster = atoi(e) == 0;
-    if (const char* e = getenv("PRV_FINE_CULL")) {  // same as prv_set_fine_cull before the first prv_set_map
-        const int k = atoi(e);  // "1", "2", "4"; "-1", "-2", "-4": the same with the march starting at the fine cell
-        if (k == 1 || k == 2 || k == 4 || k == -1 || k == -2 || k == -4) {
-            ctx->fine_k = k < 0 ? -k : k;
-            ctx->fine_entry = k < 0;
-        }
-    }
     *out = ctx;
     return PRV_OK;
 }
@@ -679,7 +666,7 @@ void prv_destroy(prv_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     prv_comm_destroy(ctx);
-    DevBuf* bufs[] = {&ctx->d_tilesum, &ctx->d_coarse, &ctx->d_fine, &ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
+    DevBuf* bufs[] = {&ctx->d_tilesum, &ctx->d_coarse, &ctx->d_bitmap, &ctx->d_bitmap_pad, &ctx->d_prefix, &ctx->d_leaf_of_raster, &ctx->d_keys, &ctx->d_rgb, &ctx->d_views, &ctx->d_view_ids,
                       &ctx->d_row_of_id, &ctx->d_bitsets, &ctx->d_counts, &ctx->d_stats, &ctx->d_queue, &ctx->d_qcount, &ctx->d_queue2, &ctx->d_queue2b, &ctx->d_tickets, &ctx->d_arrive, &ctx->d_ens_images, &ctx->d_ens_terms, &ctx->d_ens_scores, &ctx->d_row_of_id_all, &ctx->d_ing_xyz, &ctx->d_ing_rgb, &ctx->d_ing_k0,
                       &ctx->d_ing_k1, &ctx->d_ing_v0, &ctx->d_ing_v1, &ctx->d_ing_pos, &ctx->d_ing_tmp, &ctx->d_pix_hit, &ctx->d_pix_depth, &ctx->d_mask,
                       &ctx->d_voxel_pix, &ctx->d_voxel_hit, &ctx->d_points, &ctx->d_best, &ctx->d_cov[0], &ctx->d_cov[1], &ctx->d_all_rows,
@@ -720,11 +707,11 @@ int prv_set_variant(prv_ctx* ctx, int variant) {
     return PRV_OK;
 }
 
-int prv_set_fine_cull(prv_ctx* ctx, int cell, int enter_at_cell) {
+int prv_set_brick_cull(prv_ctx* ctx, int cell, int enter_at_brick) {
     if (!ctx) return PRV_ERR_INVALID;
-    if (cell != 0 && cell != 1 && cell != 2 && cell != 4) return fail(ctx, PRV_ERR_INVALID, "prv_set_fine_cull: cell must be 0 (off), 1, 2 or 4 voxels, got %d", cell);
-    ctx->fine_k = cell;
-    ctx->fine_entry = cell != 0 && enter_at_cell != 0;
+    if (cell != 4 && cell != 8 && cell != 16) return fail(ctx, PRV_ERR_INVALID, "prv_set_brick_cull: brick edge must be 4, 8 or 16 voxels, got %d", cell);
+    ctx->brick_cs = cell;
+    ctx->brick_entry = enter_at_brick != 0;
     return PRV_OK;
 }
 
@@ -757,18 +744,11 @@ static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, 
     const size_t pad_words = ((pad_rows << row_log2) + 2 * slack_bits) / 32;
     if ((pad_rows << row_log2) + 2 * slack_bits >= ((size_t)1 << 31)) return fail(ctx, PRV_ERR_UNSUPPORTED, "prv_set_map: occupancy AABB too large for the padded bitmap");
     int nc[3];
-    for (int a = 0; a < 3; a++) nc[a] = (n[a] + kCoarse - 1) / kCoarse;
+    const int cs = ctx->brick_cs;
+    for (int a = 0; a < 3; a++) nc[a] = (n[a] + cs - 1) / cs;
     const size_t coarse_words = ((size_t)nc[0] * nc[1] * nc[2] + 31) / 32 + 1;
-    const int fine_k = ctx->fine_k;
-    int nf[3] = {0, 0, 0};
-    size_t fine_words = 0;
-    if (fine_k > 0) {
-        for (int a = 0; a < 3; a++) nf[a] = (n[a] + fine_k - 1) / fine_k;
-        fine_words = ((size_t)nf[0] * nf[1] * nf[2] + 31) / 32 + 1;
-    }
     int rc;
     if ((rc = ensure(ctx, ctx->d_coarse, coarse_words * 4))) return rc;
-    if (fine_k > 0 && (rc = ensure(ctx, ctx->d_fine, fine_words * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_bitmap_pad, pad_words * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_bitmap, nwords * 4))) return rc;
     if ((rc = ensure(ctx, ctx->d_prefix, nwords * 4))) return rc;
@@ -786,7 +766,6 @@ static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, 
     }
     CU(cudaEventRecord(ctx->ev_copy, ctx->stream));  // the caller's buffers are free once this has passed
     CU(cudaMemsetAsync(ctx->d_coarse.p, 0, coarse_words * 4, ctx->stream));
-    if (fine_k > 0) CU(cudaMemsetAsync(ctx->d_fine.p, 0, fine_words * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_bitmap_pad.p, 0, pad_words * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_bitmap.p, 0, nwords * 4, ctx->stream));
     {
@@ -807,12 +786,9 @@ static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, 
         mb.prefix = ptr<uint32_t>(ctx->d_prefix);
         mb.leaf_of_raster = ptr<uint32_t>(ctx->d_leaf_of_raster);
         mb.keys = ptr<uint16_t>(ctx->d_keys);
-        mb.fine = fine_k > 0 ? ptr<uint32_t>(ctx->d_fine) : nullptr;
-        for (int a = 0; a < 3; a++) mb.nf[a] = nf[a];
-        mb.fine_k = fine_k;
-        Span sp(ctx, K_OTHER, fine_k > 0 ? 6 : 5);
+        mb.cs = cs;
+        Span sp(ctx, K_OTHER, 5);
         map_scatter_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(mb);
-        if (fine_k > 0) map_fine_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(mb);
         map_shell_kernel<<<(uint32_t)((pad_rows + 255) / 256), 256, 0, ctx->stream>>>(mb);
         const uint32_t ntiles = (uint32_t)((nwords + kPrefixTile - 1) / kPrefixTile);
         map_tilesum_kernel<<<ntiles, kPrefixThreads, 0, ctx->stream>>>(mb, ptr<uint32_t>(ctx->d_tilesum));
@@ -848,9 +824,13 @@ static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, 
     }
     ctx->map.coarse = ptr<uint32_t>(ctx->d_coarse);
     for (int a = 0; a < 3; a++) ctx->map.nc[a] = nc[a];
-    ctx->map.fine = fine_k > 0 ? ptr<uint32_t>(ctx->d_fine) : nullptr;
-    for (int a = 0; a < 3; a++) ctx->map.nf[a] = nf[a];
-    ctx->map.fine_k = fine_k;
+    ctx->map.cs = cs;
+    ctx->map.inv_cs = 1.0f / (float)cs;
+    {   // row / (n1 + 2) of the march epilogue as a multiply-high: exact while row * (n1 + 2) < 2^32
+        const uint64_t n1p = (uint64_t)n[1] + 2;
+        const uint64_t magic = (((uint64_t)1 << 32) + n1p - 1) / n1p;
+        ctx->map.n1p_magic = (pad_rows + 8) * n1p < ((uint64_t)1 << 32) && magic < ((uint64_t)1 << 32) ? (uint32_t)magic : 0u;
+    }
     ctx->map.pad_row_log2 = row_log2;
     ctx->map.pad_bit_offset = (uint32_t)slack_bits;
     for (int a = 0; a < 3; a++) {

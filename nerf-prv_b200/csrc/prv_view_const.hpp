@@ -54,6 +54,7 @@ inline void make_view_const(const ViewSetup& ctx, const double* pose_world, cons
         vc.okey[a] = k[a];
         vc.origin[a] = ok ? (float)prv::key_to_coord(k[a], ctx.resolution) : 0.0f;
     }
+    for (int a = 0; a < 3; a++) vc.tnum[a][0] = vc.tnum[a][1] = 0.0;
     if (!ok) return;
     for (int r = 0; r < 3; r++) vc.posef[4 * r + 3] = (float)(pw(r, 3) - (double)vc.origin[r]);
     vc.flags |= kViewInMap;
@@ -62,6 +63,14 @@ inline void make_view_const(const ViewSetup& ctx, const double* pose_world, cons
         uint16_t kk;
         if (prv::coord_to_key_checked((double)vc.origin[a], rf, kk)) vc.okey[a] = kk;
     }
+    // castRay's voxelBorder - origin per axis and step sign (OccupancyOcTreeBase::castRay: voxelBorder = keyToCoord(key) +
+    // step * resolution * 0.5; tMax = (voxelBorder - (double)origin) / direction), operation by operation
+    for (int a = 0; a < 3; a++)
+        for (int sgn = 0; sgn < 2; sgn++) {
+            double border = prv::key_to_coord(vc.okey[a], ctx.resolution);
+            border = border + ((double)(sgn == 0 ? 1 : -1) * ctx.resolution) * 0.5;
+            vc.tnum[a][sgn] = border - (double)vc.origin[a];
+        }
     // origin voxel occupied?
     bool inside = true;
     for (int a = 0; a < 3; a++) inside = inside && vc.okey[a] >= ctx.lo[a] && vc.okey[a] < ctx.lo[a] + ctx.n[a];

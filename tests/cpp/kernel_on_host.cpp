@@ -36,6 +36,7 @@ static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fdividef(float a, float b) { return a / b; }  // culls only
 static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }  // culls only
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
 static inline double __longlong_as_double(long long v) {
@@ -74,13 +75,13 @@ namespace {
 // the HBM tables of one map, built on the host from the documented layout
 struct HostMap {
     DevMap m{};
-    std::vector<uint32_t> bitmap, pad, coarse, fine, prefix, leaf_of_raster;
+    std::vector<uint32_t> bitmap, pad, coarse, prefix, leaf_of_raster;
     std::vector<uint16_t> keys;
     std::vector<uint8_t> rgb;
     ViewSetup setup{};
 };
 
-bool build_map(HostMap& hm, const uint16_t* keys, const uint8_t* rgb, uint32_t N, double resolution, double max_range, int fine_k = 0) {
+bool build_map(HostMap& hm, const uint16_t* keys, const uint8_t* rgb, uint32_t N, double resolution, double max_range, int brick_cs = kCoarseDefault) {
     if (N == 0) return false;
     hm.keys.assign(keys, keys + 3 * (size_t)N);
     if (rgb) hm.rgb.assign(rgb, rgb + 3 * (size_t)N); else hm.rgb.assign(3 * (size_t)N, 0);
@@ -95,7 +96,7 @@ bool build_map(HostMap& hm, const uint16_t* keys, const uint8_t* rgb, uint32_t N
     for (int a = 0; a < 3; a++) {
         m.lo[a] = lo[a];
         m.n[a] = hi[a] - lo[a] + 1;
-        m.nc[a] = (m.n[a] + kCoarse - 1) / kCoarse;
+        m.nc[a] = (m.n[a] + brick_cs - 1) / brick_cs;
         // AABB grown by 2 voxels, metres
         m.bmin[a] = (float)((double)(lo[a] - 2 - prv::kTreeMaxVal) * resolution);
         m.bmax[a] = (float)((double)(lo[a] + m.n[a] + 2 - prv::kTreeMaxVal) * resolution);
@@ -124,9 +125,13 @@ bool build_map(HostMap& hm, const uint16_t* keys, const uint8_t* rgb, uint32_t N
             for (int c0 = 0; c0 < m.n[0] + 2; c0++)
                 if (c0 == 0 || c0 == m.n[0] + 1 || c1 == 0 || c1 == m.n[1] + 1 || c2 == 0 || c2 == m.n[2] + 1) set_pad(c0, c1, c2);
     hm.coarse.assign(((size_t)m.nc[0] * m.nc[1] * m.nc[2] + 31) / 32 + 1, 0u);
-    m.fine_k = fine_k;  // optional second cull level (prv_set_fine_cull)
-    for (int a = 0; a < 3; a++) m.nf[a] = fine_k > 0 ? (m.n[a] + fine_k - 1) / fine_k : 0;
-    if (fine_k > 0) hm.fine.assign(((size_t)m.nf[0] * m.nf[1] * m.nf[2] + 31) / 32 + 1, 0u);
+    m.cs = brick_cs;  // brick edge (prv_set_brick_cull)
+    m.inv_cs = 1.0f / (float)brick_cs;
+    {
+        const uint64_t n1p = (uint64_t)m.n[1] + 2;
+        const uint64_t magic = (((uint64_t)1 << 32) + n1p - 1) / n1p;
+        m.n1p_magic = (pad_rows + 8) * n1p < ((uint64_t)1 << 32) && magic < ((uint64_t)1 << 32) ? (uint32_t)magic : 0u;
+    }
     for (uint32_t i = 0; i < N; i++) {
         const int q[3] = {keys[3 * i] - lo[0], keys[3 * i + 1] - lo[1], keys[3 * i + 2] - lo[2]};
         hm.bitmap[((size_t)q[2] * m.n[1] + q[1]) * m.wx + (q[0] >> 5)] |= 1u << (q[0] & 31);
@@ -137,12 +142,8 @@ bool build_map(HostMap& hm, const uint16_t* keys, const uint8_t* rgb, uint32_t N
                 for (int d0 = -1; d0 <= 1; d0++) {
                     const int p0 = q[0] + d0, p1 = q[1] + d1, p2 = q[2] + d2;
                     if (p0 < 0 || p1 < 0 || p2 < 0 || p0 >= m.n[0] || p1 >= m.n[1] || p2 >= m.n[2]) continue;
-                    const uint32_t c = (uint32_t)(((p2 / kCoarse) * m.nc[1] + p1 / kCoarse) * m.nc[0] + p0 / kCoarse);
+                    const uint32_t c = (uint32_t)(((p2 / brick_cs) * m.nc[1] + p1 / brick_cs) * m.nc[0] + p0 / brick_cs);
                     hm.coarse[c >> 5] |= 1u << (c & 31);
-                    if (fine_k > 0) {
-                        const uint32_t f = (uint32_t)(((p2 / fine_k) * m.nf[1] + p1 / fine_k) * m.nf[0] + p0 / fine_k);
-                        hm.fine[f >> 5] |= 1u << (f & 31);
-                    }
                 }
     }
     hm.prefix.assign(hm.bitmap.size(), 0u);
@@ -161,7 +162,6 @@ bool build_map(HostMap& hm, const uint16_t* keys, const uint8_t* rgb, uint32_t N
     m.bitmap = hm.bitmap.data();
     m.bitmap_pad = hm.pad.data();
     m.coarse = hm.coarse.data();
-    m.fine = fine_k > 0 ? hm.fine.data() : nullptr;
     m.prefix = hm.prefix.data();
     m.leaf_of_raster = hm.leaf_of_raster.data();
     m.keys = hm.keys.data();
@@ -199,12 +199,12 @@ DevCam make_cam(const prv_intrinsics& it, double max_range, int force_region_cul
 enum { S_RAYS = 0, S_REGION_CULLED, S_LOOSE_CULLED, S_COARSE_CULLED, S_MARCHED, S_PROBES, S_STEPS, S_HITS, S_FLAGS, S_REGION_OK, S_BOX_ENTRIES, S_BOX_FALLBACKS, S_N };
 
 // one pixel through stages 1b..3 of the AXIS pipeline (cull_kernel's per-pixel part, coarse_kernel, march_kernel)
-void axis_pixel(const HostMap& hm, const DevCam& cam, const ViewConst& vc, int px, int py, CastResult& res, uint64_t* st, bool entry = false) {
+void axis_pixel(const HostMap& hm, const DevCam& cam, const ViewConst& vc, int px, int py, CastResult& res, uint64_t* st, bool entry = true) {
     res.rank = kNone;
     res.steps = res.probes = 0;
     res.k0 = res.k1 = res.k2 = 0;
     const bool fast = (vc.flags & kViewFastOk) != 0;
-    uint32_t cell = kNone;  // what coarse_fine_kernel hands to march_entry_kernel through queue2b
+    uint32_t cell = kNone;  // what coarse_kernel hands to march_kernel through queue2b
     if (fast) {
         float dx, dy, dz;
         ray_direction_approx(cam, vc, (float)px, (float)py, dx, dy, dz);
@@ -212,27 +212,26 @@ void axis_pixel(const HostMap& hm, const DevCam& cam, const ViewConst& vc, int p
             st[S_LOOSE_CULLED]++;
             return;
         }
-        if (hm.m.fine_k > 0 ? coarse_miss_fine(hm.m, vc, dx, dy, dz, cell) : coarse_miss(hm.m, vc, dx, dy, dz)) {
+        if (coarse_miss(hm.m, vc, dx, dy, dz, cell)) {
             st[S_COARSE_CULLED]++;
             return;
         }
     }
     st[S_MARCHED]++;
-    RayState r;
-    float dx, dy, dz;
-    ray_direction(cam, vc, px, py, dx, dy, dz);
-    if (ray_init(vc, hm.m.resolution, dx, dy, dz, r)) {
+    if (!entry) cell = kNone;  // cast_impl passes no queue2b
+    if (cell != kNone) st[S_BOX_ENTRIES]++;
+    for (;;) {  // march_kernel's loop
+        RayState r;
+        float dx, dy, dz;
+        ray_direction(cam, vc, px, py, dx, dy, dz);
+        if (!ray_init(vc, hm.m.resolution, dx, dy, dz, r)) break;
         if (!fast) {
             march_plain(hm.m, cam, vc, r, res);
-        } else if (entry && cell != kNone) {  // march_body<ENTRY = true>
-            st[S_BOX_ENTRIES]++;
-            if (!march_axis_box(hm.m, vc, r, cell, res)) {
-                st[S_BOX_FALLBACKS]++;
-                march_axis(hm.m, vc, r, res);
-            }
-        } else {
-            march_axis(hm.m, vc, r, res);
+            break;
         }
+        if (march_axis(hm.m, vc, r, cell, res)) break;
+        st[S_BOX_FALLBACKS]++;
+        cell = kNone;
     }
 }
 
@@ -245,17 +244,16 @@ float hit_depth(const HostMap& hm, const ViewConst& vc, const CastResult& res) {
 extern "C" {
 
 // Dense cast of one view.  variant: 0 PLAIN, 1 FAST (raycast_kernel), 2 AXIS pipeline (cull / coarse / march kernels).
-// force_region_cull: -1 = as prv_set_camera decides, 0 / 1 = force off / on.  fine_k, fine_entry: prv_set_fine_cull (0 = off).
+// force_region_cull: -1 = as prv_set_camera decides, 0 / 1 = force off / on.  brick_cs, brick_entry: prv_set_brick_cull.
 // hit_rank, depth: [H][W]; stats: S_N counters.  Returns 0, or -1 for bad input.
 int koh_cast_view_dense(const uint16_t* keys, const uint8_t* rgb, uint32_t N, double resolution, const prv_intrinsics* intr, double max_range,
-                        const double* pose_world, const double* init_pos, int variant, int force_region_cull, int fine_k, int fine_entry,
+                        const double* pose_world, const double* init_pos, int variant, int force_region_cull, int brick_cs, int brick_entry,
                         uint32_t* hit_rank, float* depth, uint64_t* stats) {
     HostMap hm;
     if (!keys || !intr || !pose_world || !init_pos || !hit_rank || !depth || !stats) return -1;
-    if (fine_k != 0 && fine_k != 1 && fine_k != 2 && fine_k != 4) return -1;
-    if (!build_map(hm, keys, rgb, N, resolution, max_range, fine_k)) return -1;
-    // as cast_impl: the packed cell coordinates must fit
-    const bool entry = fine_entry && fine_k > 0 && std::max(hm.m.nf[0], std::max(hm.m.nf[1], hm.m.nf[2])) <= (1 << kFineCellBits);
+    if (brick_cs != 4 && brick_cs != 8 && brick_cs != 16) return -1;
+    if (!build_map(hm, keys, rgb, N, resolution, max_range, brick_cs)) return -1;
+    const bool entry = brick_entry != 0;
     const DevCam cam = make_cam(*intr, max_range, force_region_cull);
     ViewConst vc;
     std::memset(&vc, 0, sizeof(vc));

@@ -1,9 +1,9 @@
 // map_kernels_on_host.cpp -- TEST INFRASTRUCTURE.  Runs the barrier-free map-build kernels of kernels_map.cuh
-// (map_scatter_kernel, map_fine_kernel, map_shell_kernel, map_rank_kernel) -- the kernel source, unchanged -- on the CPU:
+// (map_scatter_kernel, map_shell_kernel, map_rank_kernel) -- the kernel source, unchanged -- on the CPU:
 // blocks and threads are executed one after the other with threadIdx / blockIdx as plain globals and atomics as plain
 // read-modify-writes, and the tables they leave must equal, word for word, the tables kernel_on_host.cpp builds from the
 // layout documented in DESIGN.md section 3 (which the per-ray checks run on).  Closes the loop for the lookup tables
-// without a GPU, in particular for the optional fine grid (prv_set_fine_cull), and runs clean under ASan.
+// without a GPU, for every brick size of prv_set_brick_cull, and runs clean under ASan.
 #include "kernel_on_host.cpp"
 
 #include <cstdlib>
@@ -65,19 +65,18 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
 extern "C" {
 
 // returns 0 when every table written by the kernels equals the host-built one; otherwise the number of the first differing table
-int mkh_check_map_kernels(const uint16_t* keys, uint32_t N, double resolution, int fine_k) {
+int mkh_check_map_kernels(const uint16_t* keys, uint32_t N, double resolution, int brick_cs) {
     HostMap hm;
-    if (!build_map(hm, keys, nullptr, N, resolution, 1.0, fine_k)) return -1;
+    if (!build_map(hm, keys, nullptr, N, resolution, 1.0, brick_cs)) return -1;
     const DevMap& m = hm.m;
     // zeroed tables of exactly the sizes prv_set_map allocates
-    std::vector<uint32_t> bitmap(hm.bitmap.size(), 0u), pad(hm.pad.size(), 0u), coarse(hm.coarse.size(), 0u), fine(hm.fine.size(), 0u);
+    std::vector<uint32_t> bitmap(hm.bitmap.size(), 0u), pad(hm.pad.size(), 0u), coarse(hm.coarse.size(), 0u);
     std::vector<uint32_t> leaf_of_raster(N, 0xDEADBEEFu);
     MapBuild b{};
     for (int a = 0; a < 3; a++) {
         b.lo[a] = m.lo[a];
         b.n[a] = m.n[a];
         b.nc[a] = m.nc[a];
-        b.nf[a] = m.nf[a];
     }
     b.wx = m.wx;
     b.row_log2 = m.pad_row_log2;
@@ -90,16 +89,13 @@ int mkh_check_map_kernels(const uint16_t* keys, uint32_t N, double resolution, i
     b.prefix = hm.prefix.data();  // host scan of the kernel-built bitmap, checked below
     b.leaf_of_raster = leaf_of_raster.data();
     b.keys = hm.keys.data();
-    b.fine = fine_k > 0 ? fine.data() : nullptr;
-    b.fine_k = fine_k;
+    b.cs = brick_cs;
     launch(dim3((N + 255) / 256), dim3(256), [&] { map_scatter_kernel(b); });
-    if (fine_k > 0) launch(dim3((N + 255) / 256), dim3(256), [&] { map_fine_kernel(b); });
     const size_t pad_rows = (size_t)(m.n[1] + 2) * (m.n[2] + 2);
     launch(dim3((unsigned)((pad_rows + 255) / 256)), dim3(256), [&] { map_shell_kernel(b); });
     if (bitmap != hm.bitmap) return 1;
     if (pad != hm.pad) return 2;
     if (coarse != hm.coarse) return 3;
-    if (fine != hm.fine) return 4;
     launch(dim3((N + 255) / 256), dim3(256), [&] { map_rank_kernel(b); });
     if (leaf_of_raster != hm.leaf_of_raster) return 5;
     return 0;

@@ -1,5 +1,5 @@
-// pipeline_on_host.cpp -- TEST INFRASTRUCTURE.  The ray-cast KERNELS of kernels_cast.cuh -- cull_kernel, coarse_kernel /
-// coarse_fine_kernel, march_kernel / march_entry_kernel, and the voxel-mode kernels, source unchanged -- run on the CPU by
+// pipeline_on_host.cpp -- TEST INFRASTRUCTURE.  The ray-cast KERNELS of kernels_cast.cuh -- cull_kernel, coarse_kernel,
+// march_kernel, and the voxel-mode kernels, source unchanged -- run on the CPU by
 // the SIMT emulator of simt_on_host.hpp: queues, tickets, ballots, block / warp barriers, atomics and the coverage-row
 // scatter execute as written, so what kernel_on_host.cpp cannot see (the plumbing between the per-ray functions) is held
 // against the oracle without a GPU too.  The launch sequence below is cast_impl's (prv_device.cu); the lookup tables are the
@@ -112,13 +112,14 @@ int poh_score_ensemble(const uint8_t* images, uint32_t V, uint32_t E, int W, int
 // Outputs: bitsets [V][words64] u64, pix_hit / pix_depth [V][GH][GW] (GW x GH = W x H dense, (W+1) x (H+1) voxel; depth only
 // dense), stats [V][4] (rays, probes, hits, steps), marched [V], voxel_hit [V][N] (voxel mode only, else may be null).
 int poh_cast_views(const uint16_t* keys, const uint8_t* rgb, uint32_t N, double resolution, const prv_intrinsics* intr, double max_range,
-                   const double* pose_world, const double* init_pos, uint32_t V, int mode, int fine_k, int fine_entry, int grid_blocks,
+                   const double* pose_world, const double* init_pos, uint32_t V, int mode, int brick_cs, int brick_entry, int grid_blocks,
                    uint64_t* bitsets_out, uint32_t* pix_hit_out, float* pix_depth_out, unsigned long long* stats_out, uint32_t* marched_out,
                    uint32_t* voxel_hit_out) {
     HostMap hm;
     if (!keys || !intr || !pose_world || !init_pos || !bitsets_out || !pix_hit_out || !stats_out || !marched_out || V == 0 || V > (uint32_t)kMaxViewsPerLaunch)
         return -1;
-    if (!build_map(hm, keys, rgb, N, resolution, max_range, fine_k)) return -1;
+    if (brick_cs != 4 && brick_cs != 8 && brick_cs != 16) return -1;
+    if (!build_map(hm, keys, rgb, N, resolution, max_range, brick_cs)) return -1;
     const DevCam cam = make_cam(*intr, max_range, -1);
     std::vector<ViewConst> views(V);
     for (uint32_t v = 0; v < V; v++) {
@@ -134,9 +135,10 @@ int poh_cast_views(const uint16_t* keys, const uint8_t* rgb, uint32_t N, double 
     p.GH = voxel ? cam.H + 1 : cam.H;
     p.pix_stride = (unsigned long long)p.GW * p.GH;
     const uint32_t words = hm.m.words64;
-    std::vector<uint32_t> bitsets32((size_t)V * words * 2, 0u), queue((size_t)V * p.pix_stride), queue2((size_t)V * p.pix_stride), queue2b, qcount(2 * (size_t)V, 0u),
+    std::vector<uint32_t> bitsets32((size_t)V * words * 2, 0u), queue((size_t)V * p.pix_stride), queue2((size_t)V * p.pix_stride), qcount(2 * (size_t)V, 0u),
         tickets(2, 0u), mask, voxel_pix;
     std::vector<unsigned long long> stats((size_t)V * 4, 0ull);
+    std::vector<uint32_t> queue2b;
     p.bitsets32 = bitsets32.data();
     p.stats = stats.data();
     p.pix_hit = pix_hit_out;
@@ -150,8 +152,7 @@ int poh_cast_views(const uint16_t* keys, const uint8_t* rgb, uint32_t N, double 
     p.tickets = tickets.data();
     p.view_base = 0;
     p.nviews = V;
-    const bool entry = fine_entry && hm.m.fine_k > 0 && std::max(hm.m.nf[0], std::max(hm.m.nf[1], hm.m.nf[2])) <= (1 << kFineCellBits);
-    if (entry) {
+    if (brick_entry) {
         queue2b.assign((size_t)V * p.pix_stride, 0u);
         p.queue2b = queue2b.data();
     }
@@ -167,14 +168,8 @@ int poh_cast_views(const uint16_t* keys, const uint8_t* rgb, uint32_t N, double 
         simt_launch(rgrid, dim3(256), [&] { cull_kernel<true>(p); });
     else
         simt_launch(rgrid, dim3(256), [&] { cull_kernel<false>(p); });
-    if (p.map.fine_k > 0)
-        simt_launch(dim3((unsigned)grid_blocks), dim3(256), [&] { coarse_fine_kernel(p); });
-    else
-        simt_launch(dim3((unsigned)grid_blocks), dim3(256), [&] { coarse_kernel(p); });
-    if (p.queue2b)
-        simt_launch(dim3((unsigned)grid_blocks), dim3(kMarchBlock), [&] { march_entry_kernel<kMarchBlock, kMarchMinBlocks>(p); });
-    else
-        simt_launch(dim3((unsigned)grid_blocks), dim3(kMarchBlock), [&] { march_kernel<kMarchBlock, kMarchMinBlocks>(p); });
+    simt_launch(dim3((unsigned)grid_blocks), dim3(256), [&] { coarse_kernel<8>(p); });
+    simt_launch(dim3((unsigned)grid_blocks), dim3(kMarchBlock), [&] { march_kernel<kMarchBlock, kMarchMinBlocks>(p); });
     if (voxel && voxel_hit_out)
         simt_launch(dim3((N + 255) / 256, V), dim3(256), [&] { gather_voxel_hits_kernel(N, voxel_pix.data(), pix_hit_out, p.pix_stride, voxel_hit_out); });
     std::memcpy(bitsets_out, bitsets32.data(), (size_t)V * words * 8);

@@ -241,3 +241,54 @@ def test_greedy_grid_barrier_path_matches_cluster_path(prv, orc, synth, monkeypa
         results.append(seq.tolist())
         c.close()
     assert results[0] == results[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n_views,size", [("C1", 4, (160, 120)), ("C1", 6, (640, 480)), ("C2", 8, (640, 480))])
+def test_brick_cull_settings_are_exact(prv, orc, synth, name, n_views, size):
+    """prv_set_brick_cull: bricks of 16 / 8 / 4 voxels, the exact march starting at the AABB face or at the first set brick of
+    the cull's walk.  Same rows, ranks, depths and greedy sequence for every setting (and as the oracle on
+    the small case); smaller bricks let fewer rays through, brick entry probes less."""
+    w = synth.build_workload(prv, name, n_views=n_views, size=size)
+    c = prv.Context(0)
+    try:
+        def run(cell, entry, mode=prv.MODE_DENSE):
+            c.set_brick_cull(cell, entry)
+            c.set_map(w["keys"], w["map_rgb"], w["resolution"])
+            c.set_camera(w["intr"], 1.0)
+            bits, counts, hit, depth = c.cast_views(w["pose_world"], w["init_pos"], mode=mode, want_hit_rank=True, want_depth=mode == prv.MODE_DENSE)
+            st = c.get_cast_stats()
+            seq, gains = c.greedy(0, 64)
+            return bits, counts, hit, depth, st, seq, gains
+        base = run(8, False)
+        if size[0] <= 160:
+            m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
+            it = orc.make_intrinsics(w["intr"].width, w["intr"].height, w["intr"].fx, w["intr"].fy, w["intr"].ppx, w["intr"].ppy, w["intr"].model,
+                                     list(w["intr"].coeffs))
+            for v in range(n_views):
+                ok, r, d = m.cast_view_dense(it, w["pose_world"][v], w["init_pos"][v])
+                assert np.array_equal(base[2][v], r) and np.array_equal(base[3][v], d)
+        prev = None
+        for cell in (16, 8, 4):
+            got = run(cell, False)
+            for a, b in zip(got[:4], base[:4]):
+                assert np.array_equal(a, b), "bricks of %d changed a result" % cell
+            assert got[5].tolist() == base[5].tolist() and got[6].tolist() == base[6].tolist()
+            assert got[4]["hits"] == base[4]["hits"] and got[4]["rays"] == base[4]["rays"] and got[4]["hits"] <= got[4]["marched"]
+            if prev is not None:
+                assert got[4]["marched"] <= prev
+            prev = got[4]["marched"]
+            ent = run(cell, True)
+            for a, b in zip(ent[:4], base[:4]):
+                assert np.array_equal(a, b), "bricks of %d with brick entry changed a result" % cell
+            assert ent[5].tolist() == base[5].tolist() and ent[6].tolist() == base[6].tolist()
+            assert ent[4]["marched"] == got[4]["marched"] and ent[4]["steps"] == got[4]["steps"] and ent[4]["hits"] == base[4]["hits"]
+            assert ent[4]["probes_in"] <= got[4]["probes_in"]
+            if cell <= 8:
+                assert ent[4]["probes_in"] < got[4]["probes_in"]
+        # voxel-driven mode goes through the same kernels
+        v1 = run(4, True, prv.MODE_VOXEL)
+        v0 = run(8, False, prv.MODE_VOXEL)
+        assert np.array_equal(v1[0], v0[0]) and np.array_equal(v1[2], v0[2])
+    finally:
+        c.close()

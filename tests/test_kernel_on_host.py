@@ -27,7 +27,7 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def cast_dense(koh, w, v, variant, max_range=1.0, force_region_cull=-1, intr=None, fine_k=0, fine_entry=False):
+def cast_dense(koh, w, v, variant, max_range=1.0, force_region_cull=-1, intr=None, brick=8, entry=True):
     it = intr if intr is not None else w["intr"]
     keys = np.ascontiguousarray(w["keys"], dtype=np.uint16)
     rgb = np.ascontiguousarray(w["map_rgb"], dtype=np.uint8)
@@ -37,7 +37,7 @@ def cast_dense(koh, w, v, variant, max_range=1.0, force_region_cull=-1, intr=Non
     depth = np.zeros((it.height, it.width), dtype=np.float32)
     st = np.zeros(len(STATS), dtype=np.uint64)
     rc = koh.koh_cast_view_dense(_p(keys, C.c_uint16), _p(rgb, C.c_uint8), C.c_uint32(len(keys)), C.c_double(w["resolution"]), C.byref(it),
-                                 C.c_double(max_range), _p(pw, C.c_double), _p(ip, C.c_double), variant, force_region_cull, fine_k, 1 if fine_entry else 0,
+                                 C.c_double(max_range), _p(pw, C.c_double), _p(ip, C.c_double), variant, force_region_cull, brick, 1 if entry else 0,
                                  _p(hit, C.c_uint32), _p(depth, C.c_float), _p(st, C.c_uint64))
     assert rc == 0
     return hit, depth, dict(zip(STATS, (int(x) for x in st)))
@@ -118,26 +118,26 @@ def test_region_cull_never_removes_a_hit(koh, prv, orc, synth):
 
 
 @pytest.mark.parametrize("name,size,views", [("C1", (640, 480), (0, 11, 31)), ("C2", (640, 480), (3, 50, 99)), ("C2", (200, 152), (0, 1, 2, 3, 4, 5))])
-def test_fine_cull_level_is_exact_and_culls_more(koh, prv, orc, synth, name, size, views):
-    """prv_set_fine_cull (second level of the brick cull, cells of 4 / 2 / 1 voxels): identical results, fewer marched rays."""
+def test_brick_entry_is_exact_for_every_brick_size(koh, prv, orc, synth, name, size, views):
+    """prv_set_brick_cull: bricks of 16 / 8 / 4 voxels, the exact march starting at the AABB face or at the first set brick --
+    identical results; smaller bricks prove more misses, brick entry probes less at the same DDA step count."""
     w = synth.build_workload(prv, name, n_views=max(views) + 1, size=size)
     for v in views:
         _, _, o_rank, o_depth, _ = oracle_view(orc, w, v)
-        _, _, base = cast_dense(koh, w, v, 2)
-        prev = base["marched"]
-        for fine_k in (4, 2, 1):
-            hit, depth, st = cast_dense(koh, w, v, 2, fine_k=fine_k)
-            assert np.array_equal(hit, o_rank) and np.array_equal(depth, o_depth), (name, v, fine_k)
-            assert st["hits"] == base["hits"] and st["marched"] >= st["hits"]
-            assert st["marched"] <= prev  # a finer grid never keeps more rays
-            assert st["region_culled"] == base["region_culled"] and st["loose_culled"] == base["loose_culled"]
-            prev = st["marched"]
-            # ... and with the exact march starting at the fine cell: same results, same DDA steps, fewer probes
-            hit_e, depth_e, st_e = cast_dense(koh, w, v, 2, fine_k=fine_k, fine_entry=True)
-            assert np.array_equal(hit_e, o_rank) and np.array_equal(depth_e, o_depth), (name, v, fine_k, "entry")
-            assert st_e["marched"] == st["marched"] and st_e["steps"] == st["steps"] and st_e["probes"] < st["probes"]
-            assert st_e["box_entries"] > 0 and st_e["box_fallbacks"] == 0
-        assert prev < base["marched"]  # cells of one voxel prove more misses than the 8-voxel bricks alone
+        prev = None
+        for brick in (16, 8, 4):
+            hit, depth, st = cast_dense(koh, w, v, 2, brick=brick, entry=False)
+            assert np.array_equal(hit, o_rank) and np.array_equal(depth, o_depth), (name, v, brick)
+            assert st["marched"] >= st["hits"] and st["box_entries"] == 0
+            if prev is not None:
+                assert st["hits"] == prev["hits"] and st["region_culled"] == prev["region_culled"] and st["loose_culled"] == prev["loose_culled"]
+            prev = st
+            hit_e, depth_e, st_e = cast_dense(koh, w, v, 2, brick=brick, entry=True)
+            assert np.array_equal(hit_e, o_rank) and np.array_equal(depth_e, o_depth), (name, v, brick, "entry")
+            assert st_e["marched"] == st["marched"] and st_e["steps"] == st["steps"] and st_e["hits"] == st["hits"]
+            assert st_e["probes"] <= st["probes"] and st_e["box_fallbacks"] == 0
+            if brick <= 8:  # (C1's flat torus sets every 16-voxel brick: the first brick a ray meets is set, nothing to skip)
+                assert st_e["probes"] < st["probes"] and st_e["box_entries"] > 0
 
 
 def test_max_range_disables_the_fast_path(koh, prv, orc, synth):
@@ -205,7 +205,7 @@ def test_reproduces_the_counters_the_b200_recorded(koh, prv, synth, name, n_view
     assert w["n_views"] == n_views
     tot = dict(rays=0, marched=0, probes=0, steps=0, hits=0)
     for v in range(n_views):
-        _, _, st = cast_dense(koh, w, v, 2)
+        _, _, st = cast_dense(koh, w, v, 2, entry=False)  # round 1 marched from the AABB face (prv_set_brick_cull(8, 0) today)
         for k in tot:
             tot[k] += st[k]
     assert tot["rays"] == rec["rays"] and tot["hits"] == rec["hits"]
@@ -298,7 +298,7 @@ def _random_scene(rng, prv, perms):
 
 
 def test_random_tie_prone_scenes(koh, prv, orc):
-    """200 random scenes (4 000 more were run once, all exact): every march variant and every fine-cull level against the
+    """200 random scenes (4 000 more were run once, all exact): every march variant and every brick-cull setting against the
     oracle.  This found the one place where the header relied on a device-only float->int conversion (NaN -> 0)."""
     rng = np.random.default_rng(20240)
     perms = _signed_permutations()
@@ -306,9 +306,9 @@ def test_random_tie_prone_scenes(koh, prv, orc):
     for case in range(200):
         w, max_range = _random_scene(rng, prv, perms)
         _, _, o_rank, o_depth, _ = oracle_view(orc, w, 0, max_range=max_range)
-        for variant, fine_k, entry in ((0, 0, 0), (1, 0, 0), (2, 0, 0), (2, 1, 0), (2, 2, 0), (2, 4, 0), (2, 1, 1), (2, 2, 1), (2, 4, 1)):
-            hit, depth, st = cast_dense(koh, w, 0, variant, max_range=max_range, fine_k=fine_k, fine_entry=bool(entry))
-            assert np.array_equal(hit, o_rank) and np.array_equal(depth, o_depth), "scene %d variant %d fine cull %d entry %d" % (case, variant, fine_k, entry)
+        for variant, brick, entry in ((0, 8, 0), (1, 8, 0), (2, 8, 0), (2, 16, 0), (2, 4, 0), (2, 16, 1), (2, 8, 1), (2, 4, 1)):
+            hit, depth, st = cast_dense(koh, w, 0, variant, max_range=max_range, brick=brick, entry=bool(entry))
+            assert np.array_equal(hit, o_rank) and np.array_equal(depth, o_depth), "scene %d variant %d brick %d entry %d" % (case, variant, brick, entry)
             assert st["box_fallbacks"] == 0
         hits += int((o_rank != 0xFFFFFFFF).sum())
         fast += 1 if st["flags"] & 4 else 0
@@ -329,15 +329,15 @@ def test_full_size_golden_views(koh, prv, synth):
     for name, views in (("C1", (0, 17)), ("C2", (0, 42, 99))):
         w = synth.build_workload(prv, name)
         for v in views:
-            for fine_k, entry in ((0, False), (1, True), (2, True)):
-                hit, depth, st = cast_dense(koh, w, v, 2, fine_k=fine_k, fine_entry=entry)
-                assert sha(hit) == cases[name]["hit_sha"][v] and sha(depth) == cases[name]["depth_sha"][v], (name, v, fine_k, entry)
+            for brick, entry in ((8, False), (8, True), (4, True)):
+                hit, depth, st = cast_dense(koh, w, v, 2, brick=brick, entry=entry)
+                assert sha(hit) == cases[name]["hit_sha"][v] and sha(depth) == cases[name]["depth_sha"][v], (name, v, brick, entry)
     c3 = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_full.json")))["samples"][0]
     w = synth.build_workload(prv, "C3")
     for k, v in enumerate(c3["views"][:3]):
-        for fine_k, entry in ((0, False), (1, True)):
-            hit, depth, st = cast_dense(koh, w, v, 2, fine_k=fine_k, fine_entry=entry)
-            assert sha(hit) == c3["hit_sha"][k] and sha(depth) == c3["depth_sha"][k], ("C3", v, fine_k, entry)
+        for brick, entry in ((8, False), (8, True)):
+            hit, depth, st = cast_dense(koh, w, v, 2, brick=brick, entry=entry)
+            assert sha(hit) == c3["hit_sha"][k] and sha(depth) == c3["depth_sha"][k], ("C3", v, brick, entry)
 
 
 def test_fast_path_proof_at_its_threshold(koh, prv, orc):
@@ -358,8 +358,8 @@ def test_fast_path_proof_at_its_threshold(koh, prv, orc):
         for f in (0.999, 0.9999999, 1.0, 1.0000001, 1.001):
             mr = far * f
             _, _, o_rank, o_depth, _ = oracle_view(orc, w, 0, max_range=mr)
-            for variant, fine_k, entry in ((1, 0, False), (2, 0, False), (2, 1, True)):
-                hit, depth, st = cast_dense(koh, w, 0, variant, max_range=mr, fine_k=fine_k, fine_entry=entry)
+            for variant, brick, entry in ((1, 8, False), (2, 8, False), (2, 4, True)):
+                hit, depth, st = cast_dense(koh, w, 0, variant, max_range=mr, brick=brick, entry=entry)
                 assert np.array_equal(hit, o_rank) and np.array_equal(depth, o_depth), (case, f, variant)
             if st["flags"] & 1 and not st["flags"] & 2:
                 held += 1 if st["flags"] & 4 else 0
@@ -378,8 +378,8 @@ def mkh(tmp_path_factory):
 
 
 def test_map_build_kernels_write_the_documented_tables(mkh, prv, synth):
-    """map_scatter_kernel / map_fine_kernel / map_shell_kernel / map_rank_kernel -- the kernel source, threads executed one
-    after the other -- must leave exactly the occupancy bitmap, shell-padded bitmap, coarse grid, fine grid and rank table that
+    """map_scatter_kernel / map_shell_kernel / map_rank_kernel -- the kernel source, threads executed one
+    after the other -- must leave exactly the occupancy bitmap, shell-padded bitmap, brick grid (every brick size) and rank table that
     the per-ray checks above run on (built on the host from the documented layout)."""
     rng = np.random.default_rng(3)
     perms = _signed_permutations()
@@ -387,9 +387,9 @@ def test_map_build_kernels_write_the_documented_tables(mkh, prv, synth):
     tables += [_random_scene(rng, prv, perms)[0] for _ in range(40)]
     for w in tables:
         keys = np.ascontiguousarray(w["keys"], dtype=np.uint16)
-        for fine_k in (0, 4, 2, 1):
-            rc = mkh.mkh_check_map_kernels(_p(keys, C.c_uint16), C.c_uint32(len(keys)), C.c_double(w["resolution"]), fine_k)
-            assert rc == 0, "table %d differs (%d voxels, fine grid %d)" % (rc, len(keys), fine_k)
+        for brick in (16, 8, 4):
+            rc = mkh.mkh_check_map_kernels(_p(keys, C.c_uint16), C.c_uint32(len(keys)), C.c_double(w["resolution"]), brick)
+            assert rc == 0, "table %d differs (%d voxels, bricks of %d)" % (rc, len(keys), brick)
 
 
 def test_voxel_mode_kernels_match_oracle(mkh, prv, orc, synth):
@@ -445,10 +445,10 @@ def poh(tmp_path_factory):
     return C.CDLL(str(out))
 
 
-CONFIGS = ((0, 0), (2, 0), (1, 1))  # (fine cull cell, enter at cell): default pipeline and the two opt-in levels
+CONFIGS = ((8, 1), (8, 0), (4, 1))  # (brick edge, enter at brick): the default pipeline, the march from the AABB face, smaller bricks
 
 
-def run_kernels(poh, w, views, mode, fine_k=0, entry=0, grid=2, max_range=1.0, intr=None):
+def run_kernels(poh, w, views, mode, brick=8, entry=1, grid=2, max_range=1.0, intr=None):
     """cull -> coarse -> march kernels (and the voxel-mode kernels) as cast_impl launches them, on the emulator."""
     it = intr if intr is not None else w["intr"]
     keys = np.ascontiguousarray(w["keys"], dtype=np.uint16)
@@ -461,7 +461,7 @@ def run_kernels(poh, w, views, mode, fine_k=0, entry=0, grid=2, max_range=1.0, i
     out = dict(bits=np.zeros((V, words), dtype=np.uint64), hit=np.zeros((V, gh, gw), dtype=np.uint32), depth=np.zeros((V, gh, gw), dtype=np.float32),
                stats=np.zeros((V, 4), dtype=np.uint64), marched=np.zeros(V, dtype=np.uint32), voxel_hit=np.zeros((V, n), dtype=np.uint32))
     rc = poh.poh_cast_views(_p(keys, C.c_uint16), _p(rgb, C.c_uint8), C.c_uint32(n), C.c_double(w["resolution"]), C.byref(it), C.c_double(max_range),
-                            _p(pw, C.c_double), _p(ip, C.c_double), C.c_uint32(V), mode, fine_k, entry, grid, _p(out["bits"], C.c_uint64),
+                            _p(pw, C.c_double), _p(ip, C.c_double), C.c_uint32(V), mode, brick, entry, grid, _p(out["bits"], C.c_uint64),
                             _p(out["hit"], C.c_uint32), _p(out["depth"], C.c_float), _p(out["stats"], C.c_ulonglong), _p(out["marched"], C.c_uint32),
                             _p(out["voxel_hit"], C.c_uint32))
     assert rc == 0
@@ -470,20 +470,20 @@ def run_kernels(poh, w, views, mode, fine_k=0, entry=0, grid=2, max_range=1.0, i
 
 @pytest.mark.parametrize("name,size,grid", [("C1", (96, 72), 2), ("C2", (64, 48), 3), ("C1", (97, 61), 1)])
 def test_cast_kernels_on_the_emulator_match_oracle(poh, koh, prv, orc, synth, name, size, grid):
-    """cull_kernel, coarse_kernel / coarse_fine_kernel, march_kernel / march_entry_kernel -- kernel source unchanged, one OS
+    """cull_kernel, coarse_kernel, march_kernel -- kernel source unchanged, one OS
     thread per CUDA thread -- against the oracle: per-pixel ranks and depths (every pixel written by exactly the kernel that
     owns it), coverage rows (the atomicOr scatter), per-view counters (the warp-reduced statistics).  Odd image size: the
     scalar no-hit store path."""
     w = synth.build_workload(prv, name, n_views=3, size=size)
     m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
     words = orc.bitset_words(m.n)
-    for fine_k, entry in CONFIGS:
-        out = run_kernels(poh, w, range(3), 1, fine_k, entry, grid)
+    for brick, entry in CONFIGS:
+        out = run_kernels(poh, w, range(3), 1, brick, entry, grid)
         for v in range(3):
             _, _, o_rank, o_depth, o_st = oracle_view(orc, w, v)
-            assert np.array_equal(out["hit"][v], o_rank) and np.array_equal(out["depth"][v], o_depth), (name, v, fine_k, entry)
+            assert np.array_equal(out["hit"][v], o_rank) and np.array_equal(out["depth"][v], o_depth), (name, v, brick, entry)
             assert np.array_equal(out["bits"][v], orc.bitset_from_ranks(o_rank, words))
-            _, _, st = cast_dense(koh, w, v, 2, fine_k=fine_k, fine_entry=bool(entry))  # the per-ray check counts the same work
+            _, _, st = cast_dense(koh, w, v, 2, brick=brick, entry=bool(entry))  # the per-ray check counts the same work
             assert out["stats"][v].tolist() == [st["rays"], st["probes"], st["hits"], st["steps"]] and out["marched"][v] == st["marched"]
             assert st["hits"] == o_st["hits"]
 
@@ -496,8 +496,8 @@ def test_cast_kernels_on_the_emulator_full_size_view(poh, prv, synth):
     case = [c for c in json.load(open(os.path.join(ROOT, "tests", "golden", "golden_full.json")))["cases"] if c["name"] == "C2"][0]
     w = synth.build_workload(prv, "C2")
     v = 37
-    for fine_k, entry in ((0, 0), (1, 1)):
-        out = run_kernels(poh, w, [v], 1, fine_k, entry, grid=4)
+    for brick, entry in ((8, 1), (4, 0)):
+        out = run_kernels(poh, w, [v], 1, brick, entry, grid=4)
         assert hashlib.sha256(out["hit"][0].tobytes()).hexdigest() == case["hit_sha"][v]
         assert hashlib.sha256(out["depth"][0].tobytes()).hexdigest() == case["depth_sha"][v]
         assert hashlib.sha256(out["bits"][0].tobytes()).hexdigest() == case["row_sha"][v]
@@ -512,11 +512,11 @@ def test_voxel_mode_kernels_on_the_emulator(poh, prv, orc, synth):
     m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
     ointr = orc.make_intrinsics(it.width, it.height, it.fx, it.fy, it.ppx, it.ppy, it.model, list(it.coeffs))
     words = orc.bitset_words(m.n)
-    for fine_k, entry in ((0, 0), (1, 1)):
-        out = run_kernels(poh, w, range(2), 0, fine_k, entry)
+    for brick, entry in ((8, 1), (4, 0)):
+        out = run_kernels(poh, w, range(2), 0, brick, entry)
         for v in range(2):
             ok, _, o_ranks = m.precept(ointr, w["pose_world"][v], w["init_pos"][v])
-            assert ok and np.array_equal(out["voxel_hit"][v], o_ranks), (v, fine_k, entry)
+            assert ok and np.array_equal(out["voxel_hit"][v], o_ranks), (v, brick, entry)
             assert np.array_equal(out["bits"][v], orc.bitset_from_ranks(o_ranks, words))
             assert (o_ranks != orc.NONE).sum() > 100
 
@@ -530,13 +530,13 @@ def test_special_views_on_the_emulator(poh, prv, orc, synth):
     w["init_pos"][1] = (k - 32768 + 0.5) * res           # "view in the object" (main.cpp:263-267)
     w["init_pos"][2] = np.array([1.0e6, 0.0, 0.0])       # "View out of map" (main.cpp:139)
     for max_range in (1.0, 0.3):
-        for fine_k, entry in ((0, 0), (1, 1)):
-            out = run_kernels(poh, w, range(4), 1, fine_k, entry, max_range=max_range)
+        for brick, entry in ((8, 1), (4, 0)):
+            out = run_kernels(poh, w, range(4), 1, brick, entry, max_range=max_range)
             for v in range(4):
                 _, _, o_rank, o_depth, _ = oracle_view(orc, w, v, max_range=max_range)
                 if v in (1, 2):  # such views launch no rays; cull_kernel still records "no hit" for every pixel
                     assert np.all(o_rank == 0xFFFFFFFF) and int(out["stats"][v][0]) == 0 and not out["bits"][v].any()
-                assert np.array_equal(out["hit"][v], o_rank) and np.array_equal(out["depth"][v], o_depth), (v, max_range, fine_k, entry)
+                assert np.array_equal(out["hit"][v], o_rank) and np.array_equal(out["depth"][v], o_depth), (v, max_range, brick, entry)
 
 
 def test_splat_kernels_on_the_emulator(poh, prv, orc, synth):
