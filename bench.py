@@ -6,14 +6,22 @@
 
 A "step" is one pass of the hot path over one object: dense per-pixel ray cast of every candidate view
 (first-hit voxel rank + depth per pixel, coverage bitset per view), per-view coverage counts, and the
-greedy set-cover selection (first view 0, num_of_max_iteration = 64).  Workload at N = 1: BASELINE config C2
-(~200k-point synthetic cloud, 0.001 m voxels, the reference's 100-view hemisphere, 640x480).  N > 1: every rank
-processes its own object of the same shape (objects sharded across GPUs as in config C4; no data-path
-collective) => weak scaling; `--workload C3` runs the 1024-view strong-scaling case with the NCCL bitset
-all-gather instead.
+greedy set-cover selection (first view 0, num_of_max_iteration = 64).
+
+Default workload at EVERY N: BASELINE config C3, the north-star's "1024-view workload" (1024 Fibonacci-hemisphere
+views at 1280x960, 1.258 G rays per step).  N = 1 casts all views on one GPU; N > 1 shards the views interleaved
+across the ranks, all-gathers the coverage rows over NCCL inside the timed step and runs the selection replicated
+=> STRONG scaling, same total work at every N.  The result of every timed run -- gathered rows, counts, greedy
+sequence, on every rank -- is compared with the CPU oracle's frozen vectors (tests/golden/golden_c3.json).
+
+At N = 1 the line also carries config C2 (BASELINE configs[1]: 100 views, 640x480, 0.001 m voxels; `c2`), the splat
+z-buffer render of C5 (`c5_splat`) and the rooflines of the march, greedy and splat kernels.
+`--workload C1|C2|C4|C5` selects another config as the headline (N > 1: one object per rank, weak scaling).
 """
 import argparse
+import hashlib
 import json
+import math
 import os
 import subprocess
 import sys
@@ -37,6 +45,7 @@ def emit(line):
 METRIC = "rays_per_sec"
 UNIT = "rays/s"
 GREEDY_MAX_ITER = 64  # DefaultConfiguration.yaml:26 num_of_max_iteration
+L2_BYTES = 126 << 20
 
 
 def _peaks():
@@ -106,16 +115,27 @@ def _dist_env():
     return rank, world, local
 
 
+def _oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    orc.build()
+    return orc
+
+
 def _oracle_intr(orc, it):
     return orc.make_intrinsics(it.width, it.height, it.fx, it.fy, it.ppx, it.ppy, it.model, list(it.coeffs))
 
 
-def cpu_sample(w, view_ids, threads):
+def _synth():
+    import load_pkg
+    load_pkg.load()  # (imports the package; libprv_b200.so itself is only dlopen'ed by the first C-ABI call)
+    from nerf_prv_b200 import synth
+    return synth
+
+
+def cpu_sample(orc, w, view_ids, threads):
     """Times the oracle (CPU restatement of the reference path) on a bounded sample of the workload: dense cast of
     `view_ids`, their coverage rows, and a greedy pass over those rows.  Returns (rays, seconds, stats)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle as orc
-    orc.build()
     m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
     it = _oracle_intr(orc, w["intr"])
     words = orc.bitset_words(m.n)
@@ -130,266 +150,422 @@ def cpu_sample(w, view_ids, threads):
     return len(view_ids) * it.width * it.height, dt, st.as_dict()
 
 
+def _workload_text(name, w):
+    return ("%s: synthetic %s cloud %d pts -> %d voxels @ %.3f m, %d hemisphere views, %dx%d, dense per-pixel cast + coverage + greedy(%d)"
+            % (name, w["name"], len(w["cloud"]), len(w["keys"]), w["resolution"], w["n_views"], w["W"], w["H"], GREEDY_MAX_ITER))
+
+
+def _config(name, w, args, world, strong, l2_note):
+    return {"workload": _workload_text(name, w), "objects_per_step": 1 if (strong or world == 1) else world, "views": w["n_views"], "width": w["W"],
+            "height": w["H"], "voxels": int(len(w["keys"])), "resolution_m": w["resolution"], "l2": l2_note,
+            "sharding": ("views interleaved over %d ranks + NCCL all-gather of the coverage rows in the timed step" % world) if strong else
+                        ("one object per rank, no collective" if world > 1 else "single GPU"),
+            "variant": args.variant, "brick": args.brick, "brick_entry": bool(args.brick_entry)}
+
+
 def run_reference(args):
-    """Reference arm: the reference's own CPU algorithm (oracle port; the reference itself cannot be compiled here,
-    see DESIGN.md) on all host threads, each step a bounded sample of the same workload."""
+    """Reference arm: the reference's own CPU algorithm on all host threads -- the oracle port (the reference itself cannot
+    be compiled here), nothing of the product: the workload is synthesised through oracle.HostShim and
+    libprv_b200.so is never loaded.  Each step casts a bounded sample of the workload's views (every view in turn over the
+    steps), sized by a calibration view so that one step takes about --ref-seconds."""
     rank, world, local = _dist_env()
     if rank != 0:
         return 0
-    import load_pkg
-    prv = load_pkg.load()
-    from nerf_prv_b200 import synth
-    w = synth.build_workload(prv, args.workload)
+    orc = _oracle()
+    synth = _synth()
+    w = synth.build_workload(orc.HostShim, args.workload)
     threads = os.cpu_count() or 1
     V = w["n_views"]
-    per_step = max(1, args.ref_views)
+    _, dt1, _ = cpu_sample(orc, w, [V // 2], threads)  # calibration (untimed)
+    per_step = int(max(1, min(V, round(args.ref_seconds / max(dt1, 1e-3)))))
     times, rays = [], 0
+    stride = max(1, V // per_step)
     for s in range(args.warmup + args.steps):
-        ids = [(s * per_step + k) * 7 % V for k in range(per_step)]
-        r, dt, _ = cpu_sample(w, ids, threads)
+        ids = [(s + k * stride) % V for k in range(per_step)]  # spread over the hemisphere, shifted every step
+        r, dt, _ = cpu_sample(orc, w, ids, threads)
         if s >= args.warmup:
             times.append(dt)
             rays += r
     total = sum(times)
     value = rays / total
-    sample = "%d of %d views of %s per step (dense cast + rows + greedy over the sampled rows), %d steps" % (per_step, V, args.workload, args.steps)
+    sample = ("%d of %d views of %s per step, spread over the hemisphere and shifted every step (dense cast + rows + greedy over the sampled rows), %d steps"
+              % (per_step, V, args.workload, args.steps))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": _config(w, args, world),
+            "ms_per_step": 1e3 * total / max(1, len(times)), "higher_is_better": True, "scaling": "strong" if args.workload == "C3" else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": _config(args.workload, w, args, 1, False, "n/a (host)"),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "product_library_loaded": any("libprv_b200" in l for l in open("/proc/self/maps"))}
     emit(line)
     return 0
 
 
-def _config(w, args, world):
-    return {"workload": "%s: synthetic %s cloud %d pts -> %d voxels @ %.3f m, %d hemisphere views, %dx%d, dense per-pixel cast + coverage + greedy(%d)"
-                        % (args.workload, w["name"], len(w["cloud"]), len(w["keys"]), w["resolution"], w["n_views"], w["W"], w["H"], GREEDY_MAX_ITER),
-            "objects_per_step": world if args.workload != "C3" else 1, "views": w["n_views"], "width": w["W"], "height": w["H"],
-            "voxels": int(len(w["keys"])), "resolution_m": w["resolution"], "l2": "flushed between timed steps (256 MiB memset, untimed)",
-            "variant": args.variant, "brick": getattr(args, "brick", 8), "brick_entry": bool(getattr(args, "brick_entry", 1))}
+class Runner:
+    """One resident workload on one ctx: the timed step, kernel timing, e2e, rooflines."""
+
+    def __init__(self, prv, name, w, args, local, dist, rank, world, strong):
+        from nerf_prv_b200 import sharding
+        self.prv, self.name, self.w, self.args, self.dist, self.rank, self.world, self.strong = prv, name, w, args, dist, rank, world, strong
+        ctx = self.ctx = prv.Context(local)
+        ctx.set_variant(args.variant)
+        ctx.set_brick_cull(args.brick, bool(args.brick_entry))  # tuning only: results are identical for every setting (include/prv.h)
+        ctx.set_map(w["keys"], w["map_rgb"], w["resolution"])
+        ctx.set_camera(w["intr"], 1.0)
+        V = self.V = w["n_views"]
+        if strong:
+            ids = self.ids = sharding.pad_view_ids(sharding.shard_view_ids(V, rank, world), V, rank, world)  # interleaved view sharding
+            real = ids < V
+            self.pose = np.ascontiguousarray(np.where(real[:, None, None], w["pose_world"][np.minimum(ids, V - 1)], np.eye(4)[None]))
+            # padded slots: a position outside the key range -> "View out of map" -> empty coverage row
+            self.init = np.ascontiguousarray(np.where(real[:, None], w["init_pos"][np.minimum(ids, V - 1)], 1.0e6))
+            import torch
+            uid = prv.comm_unique_id() if rank == 0 else bytes(128)
+            t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
+            dist.broadcast(t, 0)
+            ctx.comm_init(bytes(t.cpu().tolist()), rank, world)
+            ctx.set_views(self.pose, self.init, view_ids=ids)
+            self.local_views = int(real.sum())
+        else:
+            self.ids = None
+            self.pose, self.init = np.ascontiguousarray(w["pose_world"]), np.ascontiguousarray(w["init_pos"])
+            ctx.set_views(self.pose, self.init)
+            self.local_views = V
+        self.px = w["W"] * w["H"]
+        self.rays_local = self.local_views * self.px
+        self.rays_job = V * self.px if (strong or world == 1) else self.rays_local * world
+        # the per-pixel rank + depth tables every step rewrites (8 B per ray) dwarf the L2, so consecutive steps cannot feed
+        # on each other's cache lines; smaller working sets get an explicit flush between the timed steps
+        self.needs_flush = self.rays_local * 8 <= 2 * L2_BYTES
+
+    def step(self):
+        self.ctx.cast_async(self.prv.MODE_DENSE, want_pixels=True)
+        if self.strong:
+            self.ctx.allgather_bitsets_async()
+        self.ctx.greedy_async(0, GREEDY_MAX_ITER)
+
+    def barrier(self):
+        self.ctx.sync()
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def _max_over_ranks(self, x):
+        if self.dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(self, steps, warmup):
+        """EXACTLY `steps` steps between two device events, enqueued back to back (the scoring of step k overlaps the cast of
+        step k+1 on the ctx's second stream); barrier + synchronise on both sides; max over ranks."""
+        ctx = self.ctx
+        for _ in range(warmup):
+            self.step()
+            ctx.flush_l2()
+        self.barrier()
+        ctx.timing_reset()
+        ctx.reset_counters()
+        self.barrier()
+        if self.needs_flush:
+            total = 0.0
+            for _ in range(steps):
+                ctx.event_record(0)
+                self.step()
+                ctx.event_record(1)
+                total += ctx.event_elapsed_ms(0, 1)
+                ctx.flush_l2()  # untimed
+        else:
+            ctx.event_record(0)
+            for _ in range(steps):
+                self.step()
+            ctx.event_record(1)
+            total = ctx.event_elapsed_ms(0, 1)
+        self.barrier()
+        self.timing = ctx.get_timing()
+        self.counters = ctx.get_counters()
+        self.stats = ctx.get_cast_stats()
+        self.local_ms = total
+        return self._max_over_ranks(total)
+
+    def l2_note(self):
+        if self.needs_flush:
+            return "flushed between timed steps (256 MiB memset, untimed; steps timed one by one)"
+        return ("not flushed: every step rewrites %.2f GB of per-pixel rank + depth tables per GPU (>> 126 MB L2); steps enqueued back to back"
+                % (self.rays_local * 8 / 1e9))
+
+    def e2e(self, steps):
+        """The same step through the host-buffer C ABI: H2D of keys / colours / poses from pinned memory, D2H of the coverage
+        rows, counts and the greedy sequence, every step, inside the timed region (wall clock around synchronous calls)."""
+        prv, ctx, w = self.prv, self.ctx, self.w
+        import torch
+
+        def pinned(a):
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            return t.numpy(), t
+        keep = []
+        keys_h, t = pinned(w["keys"]); keep.append(t)
+        rgb_h, t = pinned(w["map_rgb"]); keep.append(t)
+        pw_h, t = pinned(self.pose); keep.append(t)
+        ip_h, t = pinned(self.init); keep.append(t)
+        bits_h, t = pinned(np.zeros((self.pose.shape[0], ctx.words), dtype=np.uint64)); keep.append(t)
+        cnt_h, t = pinned(np.zeros(self.pose.shape[0], dtype=np.uint32)); keep.append(t)
+
+        def one():
+            ctx.set_map(keys_h, rgb_h, w["resolution"])
+            ctx.set_camera(w["intr"], 1.0)
+            if not self.strong:
+                ctx.cast_views(pw_h, ip_h, mode=prv.MODE_DENSE, want_bitsets=True, want_counts=True, out_bitsets=bits_h, out_counts=cnt_h)
+            else:
+                ctx.set_views(pw_h, ip_h, view_ids=self.ids)
+                ctx.cast_async(prv.MODE_DENSE, False)
+                ctx.allgather_bitsets_async()
+                ctx.get_bitsets()
+                ctx.get_coverage_counts()
+            return ctx.greedy(0, GREEDY_MAX_ITER)
+        one()
+        self.barrier()
+        ctx.reset_counters()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            seq, _g = one()
+        ctx.sync()
+        dt = self._max_over_ranks(time.perf_counter() - t0)
+        c = ctx.get_counters()
+        return {"value": self.rays_job * steps / dt, "unit": UNIT, "h2d_bytes_per_step": c["h2d_bytes"] // steps, "d2h_bytes_per_step": c["d2h_bytes"] // steps,
+                "steps": steps, "host_memory": "pinned"}, seq
+
+    def rooflines(self, steps, total_ms):
+        """Dominant kernel (march_kernel): algorithmic bytes per launch / CUDA-event time per launch, SURVEY 8(d): per ray
+        4*S_in + 8 B, per view bitmap + bitset row.  S_in (in-AABB probes of the literal algorithm) is a property of the input:
+        counted once, untimed, with the FAST variant, which executes every probe of the reference algorithm."""
+        prv, ctx, timing, stats = self.prv, self.ctx, self.timing, self.stats
+        peak, peak_src = _peaks()
+        ctx.set_variant(prv.VARIANT_FAST)
+        ctx.cast_async(prv.MODE_DENSE, want_pixels=False)
+        s_in = ctx.get_cast_stats()["probes_in"]
+        ctx.set_variant(self.args.variant)
+        axis = self.args.variant == 2
+        rays = stats["rays"]
+        words = ctx.words
+        alg_total = 4 * s_in + 8 * rays + self.local_views * (ctx.map_bytes() + words * 8)
+        launches = max(1, timing["march_launches"] if axis else timing["cast_launches"])
+        march_ms = (timing["march_ms"] if axis else timing["cast_ms"]) / launches
+        pipeline_ms = (timing["cull_ms"] + timing["march_ms"]) / steps
+        # the cull / coarse kernels write the 8 B/ray "no hit" records of the rays they prove to miss; the rest is the march kernel's
+        alg_march = alg_total - 8 * (rays - stats["marched"]) if axis else alg_total
+        achieved = alg_march / (march_ms * 1e-3) / 1e9
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tf):
+            try:
+                traffic = json.load(open(tf)).get(self.name)
+            except Exception:
+                pass
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "march_kernel" if axis else "raycast_kernel", "algorithmic_bytes_per_launch": int(alg_march), "ms_per_launch": march_ms,
+                "peak_source": peak_src, "share_of_step": march_ms * launches / max(1e-9, self.local_ms), "s_in_probes": int(s_in),
+                "cast_pipeline": {"kernels": "cull_kernel+coarse_kernel+march_kernel", "algorithmic_bytes": int(alg_total), "ms": pipeline_ms,
+                                  "achieved": alg_total / (pipeline_ms * 1e-3) / 1e9, "frac": alg_total / (pipeline_ms * 1e-3) / 1e9 / peak},
+                "note": "per ray 4*S_in + 8 B, per view bitmap + bitset row (SURVEY 8(d)); the march is FP64-add / issue bound, its DRAM traffic is ~2 % of "
+                        "these bytes (DESIGN.md section 7): a work rate expressed in bytes, not a bandwidth"}
+        # scoring path: per view scored per iteration its row (8*words B) + the covered mask amortised over the table (SURVEY 8(d))
+        nrows = self.V if (self.strong or self.world == 1) else self.V
+        n_sel = self.greedy_len
+        scored = sum(max(nrows - 1 - k, 0) for k in range(min(n_sel, GREEDY_MAX_ITER)))
+        iters = max(1, min(n_sel, GREEDY_MAX_ITER))
+        g_ms = timing["greedy_ms"] / max(1, timing["greedy_launches"]) * (timing["greedy_launches"] / steps)
+        g_bytes = scored * words * 8 + iters * words * 8
+        g_ach = g_bytes / (g_ms * 1e-3) / 1e9
+        roof_g = {"bound": "hbm", "kernel": ["greedy_cluster_kernel", "greedy_persistent_kernel", "greedy_iter_kernel"][max(0, ctx.greedy_path)],
+                  "algorithmic_bytes_per_step": int(g_bytes), "ms_per_step": g_ms, "achieved": g_ach, "peak": peak, "unit": "GB/s", "frac": g_ach / peak,
+                  "views_scored_per_step": int(scored), "iterations": int(iters), "us_per_iteration": 1e3 * g_ms / iters,
+                  "note": "the table lives in the cluster's shared memory: no HBM traffic after the first pass; the selection is a chain of dependent "
+                          "arg-max exchanges (one per pick), so its floor is iterations x exchange latency, not bytes / bandwidth (DESIGN.md 4.4)"}
+        return roof, roof_g, scored
+
+
+def _sha_rows(rows):
+    return hashlib.sha256(np.ascontiguousarray(rows).tobytes()).hexdigest()
+
+
+def parity_c3(runner, golden):
+    """Every rank: the table its selection ran over (its own rows at N = 1, the all-gathered table at N > 1) re-ordered by view
+    id, the coverage counts and the greedy result against the oracle's frozen full-size C3 vectors."""
+    ctx, V = runner.ctx, runner.V
+    seq, gains, cov = ctx.get_greedy()
+    if runner.strong:
+        rows, ids = ctx.get_gathered()
+        table = np.zeros((V, ctx.words), dtype=np.uint64)
+        real = ids < V
+        table[ids[real]] = rows[real]
+        pad_empty = bool(np.all(rows[~real] == 0)) if (~real).any() else True
+    else:
+        table = ctx.get_bitsets()
+        pad_empty = True
+    counts = np.unpackbits(table.view(np.uint8), axis=1).sum(axis=1)
+    res = {"rows_sha": _sha_rows(table) == golden["rows_sha"], "counts": counts.tolist() == golden["counts"], "padding_rows_empty": pad_empty,
+           "greedy_seq": seq.tolist() == golden["greedy_seq"], "greedy_gain": gains.tolist() == golden["greedy_gain"],
+           "covered_sha": hashlib.sha256(cov.tobytes()).hexdigest() == golden["covered_sha"]}
+    res["ok"] = all(res.values())
+    return res, seq, gains
+
+
+def measure(prv, synth, name, args, local, dist, rank, world, want_cpu, emit_golden=True):
+    strong = name == "C3" and world > 1
+    obj_index = rank if name == "C4" else 0
+    w = synth.build_workload(prv, name, obj_index=obj_index)
+    R = Runner(prv, name, w, args, local, dist, rank, world, strong)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    total_ms = R.timed(args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    value = R.rays_job * args.steps / (total_ms * 1e-3)
+    timing, stats = R.timing, R.stats
+
+    # ---- parity gate on the timed configuration
+    parity = None
+    seq, gains, _ = R.ctx.get_greedy()
+    R.greedy_len = len(seq)
+    gpath = os.path.join(ROOT, "tests", "golden", "golden_c3.json")
+    if name == "C3" and os.path.exists(gpath) and not args.no_parity:
+        golden = json.load(open(gpath))["cases"][0]
+        mine, seq, gains = parity_c3(R, golden)
+        if dist is not None:
+            allr = [None] * world
+            dist.all_gather_object(allr, mine)
+        else:
+            allr = [mine]
+        parity = {"golden": "tests/golden/golden_c3.json (CPU oracle, all 1024 views, 1.258 G rays)", "ranks_ok": [bool(r["ok"]) for r in allr],
+                  "checks": {k: all(r[k] for r in allr) for k in mine if k != "ok"}, "ok": all(r["ok"] for r in allr)}
+
+    # ---- a sustained region of >= 1 s when the K contract steps are shorter than that
+    sustained = None
+    step_s = total_ms * 1e-3 / args.steps
+    if total_ms < 1000.0 and not args.no_sustained:
+        n = int(min(20000, max(args.steps, math.ceil(1.05 / step_s))))
+        keep_t, keep_s, keep_c, keep_l = R.timing, R.stats, R.counters, R.local_ms
+        ms = R.timed(n, 0)
+        sustained = {"steps": n, "seconds": ms * 1e-3, "ms_per_step": ms / n, "value": R.rays_job * n / (ms * 1e-3), "unit": UNIT}
+        R.timing, R.stats, R.counters, R.local_ms = keep_t, keep_s, keep_c, keep_l
+
+    # ---- end to end through the host-buffer C ABI
+    e2e, e_seq = R.e2e(max(20, min(args.steps, 50)))
+    assert e_seq.tolist() == seq.tolist(), "e2e and resident paths disagree"
+
+    per_rank = None
+    if dist is not None:
+        mine = {"rank": rank, "step_ms": R.local_ms / args.steps, "cast_ms": timing["cast_ms"] / args.steps, "greedy_ms": timing["greedy_ms"] / args.steps,
+                "allgather_ms": timing["gather_ms"] / args.steps, "marched": stats["marched"], "local_views": R.local_views}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
+    if rank != 0:
+        R.ctx.close()
+        return None
+
+    roof, roof_g, scored = R.rooflines(args.steps, total_ms)
+    cpu = None
+    if want_cpu:
+        orc = _oracle()
+        threads = os.cpu_count() or 1
+        V = w["n_views"]
+        _, dt1, _ = cpu_sample(orc, w, [V // 2], threads)
+        nv = int(max(2, min(V, round(15.0 / max(dt1, 1e-3)))))
+        sample_ids = sorted(set(int(i) for i in np.linspace(0, V - 1, nv).astype(int)))
+        r, dt, _ = cpu_sample(orc, w, sample_ids, threads)
+        cpu = {"value": r / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d of %d views of %s (dense cast + rows + greedy over the sampled rows), %.1f s" % (len(sample_ids), V, name, dt)}
+    greedy_ms = timing["greedy_ms"] / args.steps
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if (strong or (name == "C3" and world == 1)) else "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": _config(name, w, args, world, strong, R.l2_note()),
+            "e2e": e2e, "gpu_launches": R.counters["kernel_launches"], "clocks": clocks, "roofline": roof, "roofline_greedy": roof_g,
+            "cpu_baseline": cpu, "parity": parity, "sustained": sustained,
+            "views_scored_per_sec": scored * (1 if (strong or world == 1) else world) / max(1e-9, greedy_ms * 1e-3),
+            "kernel_ms_per_step": {k: timing[k] / args.steps for k in ("cast_ms", "cull_ms", "march_ms", "count_ms", "greedy_ms", "gather_ms", "other_ms")},
+            "per_rank": per_rank, "cast_stats": stats, "greedy_len": int(len(seq)), "greedy_seq": [int(x) for x in seq],
+            "coverage_rate": float(gains.sum()) / max(1, R.ctx.full_voxels)}
+    R.ctx.close()
+    return line
+
+
+def measure_c5_splat(prv, synth, args, local):
+    """Config C5's render leg inside a timed step: the splat z-buffer of 100 views at 800x800 (points -> 64-bit atomicMin on
+    packed depth|index -> resolve to RGBA + depth), poses resident.  Algorithmic bytes per view:
+    16 P + W H (8 clear + 8 resolve-read + 4 rgba + 4 depth)."""
+    w = synth.build_workload(prv, "C5")
+    ctx = prv.Context(local)
+    ctx.set_map(w["keys"], w["map_rgb"], w["resolution"])
+    ctx.set_camera(w["intr"], 1.0)
+    ctx.set_views(w["pose_world"], w["init_pos"])
+    ctx.set_cloud(w["cloud"], w["cloud_rgb"])
+    V, P, px = w["n_views"], len(w["cloud"]), w["W"] * w["H"]
+    for _ in range(3):
+        ctx.render_async(V, 5)
+    ctx.sync()
+    ctx.timing_reset()
+    steps = max(20, args.steps)
+    ctx.event_record(0)
+    for _ in range(steps):
+        ctx.render_async(V, 5)  # (each step writes 0.5 GB of corner cells + 0.5 GB of images: >> L2)
+    ctx.event_record(1)
+    ms = ctx.event_elapsed_ms(0, 1) / steps
+    t = ctx.get_timing()
+    peak, _ = _peaks()
+    alg = V * (16 * P + px * 24)
+    ctx.close()
+    return {"workload": "C5 render leg: %d views %dx%d, %d points, point_size 5" % (V, w["W"], w["H"], P), "steps": steps, "ms_per_step": ms,
+            "views_per_sec": V / (ms * 1e-3), "pixels_per_sec": V * px / (ms * 1e-3),
+            "kernel_ms_per_step": {"splat_points_ms": t["splat_ms"] / steps, "splat_resolve_ms": t["resolve_ms"] / steps},
+            "roofline_splat": {"bound": "hbm", "kernels": "memset(corner)+splat_points_kernel+splat_resolve_kernel", "algorithmic_bytes_per_step": int(alg),
+                               "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak}}
 
 
 def run_own(args):
     rank, world, local = _dist_env()
     import load_pkg
     prv = load_pkg.load()
-    from nerf_prv_b200 import synth
+    synth = _synth()
     dist = None
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    strong = args.workload == "C3" and world > 1
-    from nerf_prv_b200 import sharding
-    # every rank its own object (weak scaling) except in the C3 strong-scaling mode
-    obj_index = rank if args.workload == "C4" else 0
-    w = synth.build_workload(prv, args.workload, obj_index=obj_index)
-    ctx = prv.Context(local)
-    ctx.set_variant(args.variant)
-    ctx.set_brick_cull(args.brick, bool(args.brick_entry))  # tuning only: results are identical for every setting (include/prv.h)
-    ctx.set_map(w["keys"], w["map_rgb"], w["resolution"])
-    ctx.set_camera(w["intr"], 1.0)
-    V = w["n_views"]
-    if strong:
-        ids = sharding.pad_view_ids(sharding.shard_view_ids(V, rank, world), V, rank, world)  # interleaved view sharding
-        real = ids < V
-        shard_pose = np.where(real[:, None, None], w["pose_world"][np.minimum(ids, V - 1)], np.eye(4)[None])
-        # padded slots: a position outside the key range -> "View out of map" -> empty coverage row
-        shard_init = np.where(real[:, None], w["init_pos"][np.minimum(ids, V - 1)], 1.0e6)
-        if rank == 0:
-            uid = prv.comm_unique_id()
-        else:
-            uid = bytes(128)
-        import torch
-        t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
-        dist.broadcast(t, 0)
-        ctx.comm_init(bytes(t.cpu().tolist()), rank, world)
-        ctx.set_views(shard_pose, shard_init, view_ids=ids)
-        local_views = int(real.sum())
-    else:
-        ctx.set_views(w["pose_world"], w["init_pos"])
-        local_views = V
-    rays_per_step_local = local_views * w["W"] * w["H"]
-
-    def step():
-        ctx.cast_async(prv.MODE_DENSE, want_pixels=True)
-        if strong:
-            ctx.allgather_bitsets_async()
-        ctx.greedy_async(0, GREEDY_MAX_ITER)
-
-    def barrier():
-        ctx.sync()
-        if dist is not None:
-            dist.barrier()
-
-    for _ in range(args.warmup):
-        step()
-        ctx.flush_l2()
-    barrier()
-    sampler = ClockSampler(local)
+    line = measure(prv, synth, args.workload, args, local, dist, rank, world, want_cpu=not args.no_cpu_baseline)
+    if rank == 0 and world == 1 and not args.no_extras:
+        # the other single-GPU configurations of BASELINE.json, in the same line
+        if args.workload != "C2":
+            sub = argparse.Namespace(**vars(args))
+            sub.steps, sub.no_sustained = max(args.steps, 50), True
+            c2 = measure(prv, synth, "C2", sub, local, None, 0, 1, want_cpu=False)
+            line["c2"] = {k: c2[k] for k in ("value", "unit", "steps", "ms_per_step", "config", "e2e", "roofline", "roofline_greedy", "kernel_ms_per_step",
+                                             "cast_stats", "views_scored_per_sec", "greedy_len", "coverage_rate")}
+        line["c5_splat"] = measure_c5_splat(prv, synth, args, local)
+        if not args.no_cpu_baseline:
+            # BASELINE.md section 3 (i): the reference's own execution structure (one std::thread per voxel in batches of
+            # num_of_thread = 20, pose inverse per voxel, sparse lookup; main.cpp:124-130, 238-284) on one view of C1
+            try:
+                orc = _oracle()
+                w1 = synth.build_workload(prv, "C1", n_views=1)
+                m1 = orc.Map.from_keys(w1["keys"], w1["map_rgb"], w1["resolution"])
+                t0 = time.perf_counter()
+                m1.precept_threads(_oracle_intr(orc, w1["intr"]), w1["pose_world"][0], w1["init_pos"][0], 1.0, 20)
+                dt = time.perf_counter() - t0
+                line["cpu_reference_structure"] = {"value": m1.n / dt, "unit": "voxel rays/s", "structure": "std::thread per voxel, batches of 20, joined per batch",
+                                                   "sample": "Perception_3D::precept of 1 view of C1 (%d voxels), %.2f s" % (m1.n, dt)}
+            except Exception as exc:  # never let the side baseline break the bench line
+                line["cpu_reference_structure"] = {"error": str(exc)}
     if rank == 0:
-        sampler.start()
-    ctx.timing_reset()
-    ctx.reset_counters()
-    step_ms = []
-    barrier()
-    for _ in range(args.steps):
-        ctx.event_record(0)
-        step()
-        ctx.event_record(1)
-        step_ms.append(ctx.event_elapsed_ms(0, 1))  # CUDA events on the launching stream
-        ctx.flush_l2()                              # untimed: next step starts with a cold L2
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    timing = ctx.get_timing()
-    counters = ctx.get_counters()
-    stats = ctx.get_cast_stats()
-    total_ms = float(sum(step_ms))
+        emit(line)
     if dist is not None:
-        import torch
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    rays_total = (rays_per_step_local * world if not strong else V * w["W"] * w["H"]) * args.steps
-    value = rays_total / (total_ms * 1e-3)
-    seq, gains, _ = ctx.get_greedy(GREEDY_MAX_ITER)
-    views_scored = sum(max(V - 1 - k, 0) for k in range(min(len(seq), GREEDY_MAX_ITER)))
-
-    # ---- end-to-end through the host-buffer C ABI: H2D of the map + poses, D2H of bitsets, counts, greedy sequence
-    e2e_steps = max(1, min(args.steps, 5))
-    pw = np.ascontiguousarray(w["pose_world"] if not strong else shard_pose)
-    ip = np.ascontiguousarray(w["init_pos"] if not strong else shard_init)
-    try:
-        import torch
-        def pinned(a):
-            t = torch.from_numpy(a).pin_memory()
-            return t.numpy(), t
-        keys_h, _k = pinned(np.ascontiguousarray(w["keys"]))
-        rgb_h, _r = pinned(np.ascontiguousarray(w["map_rgb"]))
-        pw_h, _p = pinned(pw)
-        ip_h, _i = pinned(ip)
-        # result buffers of the step (coverage rows + counts) are caller-owned pinned memory too
-        bits_h, _b = pinned(np.zeros((pw.shape[0], ctx.words), dtype=np.uint64))
-        cnt_h, _c = pinned(np.zeros(pw.shape[0], dtype=np.uint32))
-        pinned_note = "pinned"
-    except Exception:
-        keys_h, rgb_h, pw_h, ip_h = w["keys"], w["map_rgb"], pw, ip
-        bits_h = cnt_h = None
-        pinned_note = "pageable"
-    def e2e_step():
-        ctx.set_map(keys_h, rgb_h, w["resolution"])
-        ctx.set_camera(w["intr"], 1.0)
-        if not strong:
-            ctx.cast_views(pw_h, ip_h, mode=prv.MODE_DENSE, want_bitsets=True, want_counts=True, out_bitsets=bits_h, out_counts=cnt_h)
-        else:
-            ctx.set_views(pw_h, ip_h, view_ids=ids)
-            ctx.cast_async(prv.MODE_DENSE, False)
-            ctx.allgather_bitsets_async()
-            ctx.get_bitsets()
-            ctx.get_coverage_counts()
-        return ctx.greedy(0, GREEDY_MAX_ITER)
-    e2e_step()
-    barrier()
-    ctx.reset_counters()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e_seq, _g = e2e_step()
-    ctx.sync()
-    e2e_dt = time.perf_counter() - t0
-    c2 = ctx.get_counters()
-    if dist is not None:
-        import torch
-        t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_dt = float(t.item())
-    e2e_value = (rays_per_step_local * world if not strong else V * w["W"] * w["H"]) * e2e_steps / e2e_dt
-    assert e_seq.tolist() == seq.tolist(), "e2e and resident paths disagree"
-
-    per_rank = None
-    if dist is not None:
-        mine = {"rank": rank, "step_ms": float(sum(step_ms)) / args.steps, "cast_ms": timing["cast_ms"] / args.steps,
-                "greedy_ms": timing["greedy_ms"] / args.steps, "allgather_ms": timing["other_ms"] / args.steps, "marched": stats["marched"]}
-        per_rank = [None] * world
-        dist.all_gather_object(per_rank, mine)
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
-
-    # ---- roofline of the dominant kernel (march_kernel): algorithmic bytes per launch / CUDA-event time per launch.
-    # S_in (in-AABB probes of the literal algorithm) is a property of the input: it is counted once, untimed, with the
-    # FAST variant, which executes every probe of the reference algorithm (the AXIS pipeline proves some misses cheaper).
-    peak, peak_src = _peaks()
-    bitmap_bytes = ctx.map_bytes()
-    ctx.set_variant(prv.VARIANT_FAST)
-    ctx.cast_async(prv.MODE_DENSE, want_pixels=False)
-    s_in = ctx.get_cast_stats()["probes_in"]
-    ctx.set_variant(args.variant)
-    per_launch_rays = stats["rays"]
-    alg_total = 4 * s_in + 8 * per_launch_rays + local_views * (bitmap_bytes + ctx.words * 8)
-    launches = max(1, timing["march_launches"] if args.variant == 2 else timing["cast_launches"])
-    march_ms = (timing["march_ms"] if args.variant == 2 else timing["cast_ms"]) / launches
-    # cull + coarse + march of one step (the K_CULL span holds two launches per step: cull_kernel and coarse_kernel)
-    pipeline_ms = (timing["cull_ms"] + timing["march_ms"]) / args.steps
-    # the cull kernel writes the 8 B/ray "no hit" records of the rays it proves to miss; everything else is the march kernel's
-    alg_march = alg_total - 8 * (per_launch_rays - stats["marched"]) if args.variant == 2 else alg_total
-    achieved = alg_march / (march_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "march_kernel" if args.variant == 2 else "raycast_kernel", "algorithmic_bytes_per_launch": int(alg_march),
-                "ms_per_launch": march_ms, "peak_source": peak_src, "share_of_step": march_ms * launches / total_ms,
-                "s_in_probes": int(s_in),
-                "cast_pipeline": {"kernels": "cull_kernel+coarse_kernel+march_kernel", "algorithmic_bytes": int(alg_total), "ms": pipeline_ms,
-                                  "achieved": alg_total / (pipeline_ms * 1e-3) / 1e9, "frac": alg_total / (pipeline_ms * 1e-3) / 1e9 / peak},
-                "note": "per ray 4*S_in + 8 B, per view bitmap + bitset row (SURVEY 8(d)); the march is FP64-add/issue bound, not bandwidth bound (DESIGN.md)"}
-    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file):
-        try:
-            roofline["traffic"] = json.load(open(traffic_file)).get(args.workload)
-        except Exception:
-            pass
-
-    # ---- CPU baseline beside it: the oracle on a bounded sample of the same workload
-    cpu = None
-    if not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        sample_ids = [int(i) for i in np.linspace(0, V - 1, args.cpu_views).astype(int)]
-        r, dt, cst = cpu_sample(w, sample_ids, threads)
-        cpu = {"value": r / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d of %d views of %s (dense cast + rows + greedy over the sampled rows), %.1f s" % (len(sample_ids), V, args.workload, dt)}
-
-    # BASELINE.md section 3 (i): the reference's own execution structure (one std::thread per voxel in batches of
-    # num_of_thread = 20, pose inverse per voxel, sparse lookup; main.cpp:124-130, 238-284) on one view of C1
-    ref_structure = None
-    if not args.no_cpu_baseline:
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import oracle as orc
-            w1 = synth.build_workload(prv, "C1", n_views=1)
-            m1 = orc.Map.from_keys(w1["keys"], w1["map_rgb"], w1["resolution"])
-            t0 = time.perf_counter()
-            m1.precept_threads(_oracle_intr(orc, w1["intr"]), w1["pose_world"][0], w1["init_pos"][0], 1.0, 20)
-            dt = time.perf_counter() - t0
-            ref_structure = {"value": m1.n / dt, "unit": "voxel rays/s", "sample": "Perception_3D::precept of 1 view of C1 (%d voxels), %.2f s" % (m1.n, dt),
-                             "structure": "std::thread per voxel, batches of 20, joined per batch"}
-        except Exception as exc:  # never let the side baseline break the bench line
-            ref_structure = {"error": str(exc)}
-
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": _config(w, args, world),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": c2["h2d_bytes"] // e2e_steps, "d2h_bytes_per_step": c2["d2h_bytes"] // e2e_steps,
-                    "steps": e2e_steps, "host_memory": pinned_note},
-            "gpu_launches": counters["kernel_launches"], "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-            "cpu_reference_structure": ref_structure,
-            "views_scored_per_sec": views_scored * world / max(1e-9, timing["greedy_ms"] / args.steps * 1e-3) if not strong else
-                                    views_scored / max(1e-9, timing["greedy_ms"] / args.steps * 1e-3),
-            "kernel_ms_per_step": {k: timing[k] / args.steps for k in ("cast_ms", "cull_ms", "march_ms", "count_ms", "greedy_ms", "other_ms")},
-            "per_rank": per_rank, "cast_stats": stats, "greedy_len": int(len(seq)), "greedy_seq": [int(x) for x in seq], "coverage_rate": float(gains.sum()) / max(1, ctx.full_voxels)}
-    emit(line)
-    if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and line.get("parity") and not line["parity"]["ok"]:
+        sys.stderr.write("bench.py: PARITY FAILED against tests/golden/golden_c3.json: %s\n" % json.dumps(line["parity"]))
+        return 3
     return 0
 
 
@@ -403,16 +579,18 @@ def main():
         os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--workload", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
+    ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--variant", type=int, default=2)
     ap.add_argument("--brick", type=int, default=8, choices=[4, 8, 16], help="prv_set_brick_cull: brick edge of the conservative cull in voxels")
     ap.add_argument("--brick-entry", type=int, default=1, choices=[0, 1], help="prv_set_brick_cull: start the exact march at the first set brick")
-    ap.add_argument("--cpu-views", type=int, default=16, help="views in the cpu_baseline sample (~10-30 s of CPU work across the host cores)")
-    ap.add_argument("--ref-views", type=int, default=2, help="views per step of the reference arm")
+    ap.add_argument("--ref-seconds", type=float, default=6.0, help="reference arm: CPU seconds per step (sets the views sampled per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="N = 1: skip the C2 / C5 sub-measurements")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "own" else args.warmup
     if args.impl == "reference":

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PRV_ABI_VERSION 1
+#define PRV_ABI_VERSION 2
 #define PRV_NONE 0xFFFFFFFFu /* "no voxel" in hit-rank tables */
 
 typedef enum prv_status {
@@ -101,6 +101,8 @@ typedef struct prv_timing {
     float    splat_ms;    uint32_t splat_launches;
     float    resolve_ms;  uint32_t resolve_launches;
     float    other_ms;    uint32_t other_launches;
+    float    gather_ms;   uint32_t gather_launches;  /* NCCL all-gather of the coverage rows (scoring stream) */
+    uint32_t dropped;     /* spans not recorded because 65536 were already held: call prv_timing_reset more often */
 } prv_timing;
 
 /* ---------------------------------------------------------------- lifecycle */
@@ -157,7 +159,8 @@ int prv_get_map(prv_ctx* ctx, uint16_t* keys_out /* N x 3 or NULL */, uint8_t* r
 int prv_set_camera(prv_ctx* ctx, const prv_intrinsics* intr, double max_range);
 /* candidate views: view_pose_world (main.cpp:109) and View::init_pos (snapped to a voxel centre on upload, main.cpp:112-114) */
 int prv_set_views(prv_ctx* ctx, const double* pose_world /* V x 16 */, const double* init_pos /* V x 3 */, uint32_t V);
-/* multi-GPU view sharding: global id of each local view (ties in the greedy argmax break on this id). NULL = 0..V-1 */
+/* multi-GPU view sharding: global id of each local view (ties in the greedy argmax break on this id).  ids must be distinct
+ * and below 2^24; the next prv_set_views must pass the same V.  NULL (or V = 0) = 0..V-1. */
 int prv_set_view_ids(prv_ctx* ctx, const uint32_t* ids, uint32_t V);
 
 uint32_t prv_full_voxels(const prv_ctx* ctx);  /* share_data->full_voxels (main.cpp:1055-1058) */
@@ -165,7 +168,10 @@ uint32_t prv_bitset_words(const prv_ctx* ctx); /* u64 words per coverage row (pa
 uint32_t prv_num_views(const prv_ctx* ctx);
 
 /* ---------------------------------------------------------------- resident path (inputs already in HBM)
- * Kernels are enqueued on the ctx stream and the call returns without synchronising. */
+ * Kernels are enqueued and the call returns without synchronising.  The ctx owns two streams: the cast runs on one, the
+ * consumers of its coverage rows (prv_allgather_bitsets_async, prv_greedy_async) on the other, with the rows double-
+ * buffered -- a caller that enqueues cast / [all-gather] / greedy for several steps back to back gets the scoring of step k
+ * overlapped with the cull and march of step k+1.  Every prv_get_* / prv_sync / prv_event_record joins both streams. */
 int prv_cast_async(prv_ctx* ctx, int mode, int want_pixels /* also write per-pixel hit rank + depth */);
 int prv_greedy_async(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter);
 
@@ -175,7 +181,12 @@ int prv_get_coverage_counts(prv_ctx* ctx, uint32_t* out /* V */);
 /* dense: [V][H][W]; voxel mode: per-voxel [V][full_voxels] (rank seen by voxel i's ray) */
 int prv_get_hit_rank(prv_ctx* ctx, uint32_t view_begin, uint32_t view_count, uint32_t* out);
 int prv_get_depth(prv_ctx* ctx, uint32_t view_begin, uint32_t view_count, float* out); /* dense only */
-int prv_get_greedy(prv_ctx* ctx, uint32_t* seq, uint32_t* gains, uint32_t* n_out, uint64_t* covered_out /* words, may be NULL */);
+/* seq / gains hold `capacity` entries; *n_out = entries selected (<= max_iter + 1 of the prv_greedy_async call).  If that is
+ * more than `capacity` nothing is written and PRV_ERR_INVALID is returned (*n_out still tells the size needed). */
+int prv_get_greedy(prv_ctx* ctx, uint32_t* seq, uint32_t* gains, uint32_t capacity, uint32_t* n_out, uint64_t* covered_out /* words, may be NULL */);
+/* which implementation the last prv_greedy_async launched: 0 = one thread-block cluster (table in distributed shared memory),
+ * 1 = cooperative grid-barrier kernel, 2 = one launch per iteration; -1 without a ctx */
+int prv_greedy_path(const prv_ctx* ctx);
 int prv_get_cast_stats(prv_ctx* ctx, prv_cast_stats* out);
 
 /* ---------------------------------------------------------------- host-buffer one-call API (what the classes bind) */
@@ -188,8 +199,8 @@ int prv_cast_views(prv_ctx* ctx, const double* pose_world, const double* init_po
 int prv_precept(prv_ctx* ctx, const double pose_world[16], const double init_pos[3], prv_point_xyzrgb* points_out,
                 int* view_in_map_out);
 /* greedy set-cover over the resident bitsets (frozen definition; tie rule of main.cpp:2006,2088,2152).
- * seq/gains need max_iter+1 entries. */
-int prv_greedy(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter, uint32_t* seq, uint32_t* gains, uint32_t* n_out);
+ * seq / gains hold `capacity` entries (max_iter + 1 always suffices; fewer is an error only if more get selected). */
+int prv_greedy(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter, uint32_t* seq, uint32_t* gains, uint32_t capacity, uint32_t* n_out);
 
 /* ---------------------------------------------------------------- splat z-buffer render (replaces Perception_3D::render, main.cpp:68-96) */
 /* share_data->cloud_ground_truth (main.cpp:38) */
@@ -198,6 +209,11 @@ int prv_set_cloud(prv_ctx* ctx, const float* xyz /* P x 3 */, const uint8_t* rgb
  * 180-degree flip (main.cpp:1616) applied, i.e. it is the pixel content of rgbaClip_<i>.png.  depth_out [V][H][W] may be NULL. */
 int prv_render_views(prv_ctx* ctx, const double* pose_world, uint32_t V, int point_size, uint8_t* rgba_out,
                      float* depth_out);
+/* Size-augmentation probe of the NBV_Net_Labeler constructor (main.cpp:873-938): renders the V test views like
+ * prv_render_views, counts on the device the pixels that are not (255,255,255) and returns the mean over the views of
+ * count / (W*H) (main.cpp:913-931: the value compared with object_pixel_rate).  Nothing but V counters leaves the device.
+ * counts_out [V] may be NULL. */
+int prv_object_pixel_rate(prv_ctx* ctx, const double* pose_world, uint32_t V, int point_size, double* rate_out, uint32_t* counts_out);
 int prv_render_async(prv_ctx* ctx, uint32_t V, int point_size); /* resident: uses prv_set_views poses, output stays on device */
 float prv_splat_focal(const prv_intrinsics* intr);
 
@@ -231,6 +247,9 @@ int prv_comm_init(prv_ctx* ctx, const void* id_128, int rank, int nranks);
 /* all-gathers the local coverage rows (equal V on every rank, view ids from prv_set_view_ids) so every rank
  * holds the full table; the greedy then runs replicated and deterministic on every rank. */
 int prv_allgather_bitsets_async(prv_ctx* ctx);
+/* the table the replicated selection runs over after the all-gather: nranks * V rows in rank order and their view ids
+ * (rows_out [nrows][words], ids_out [nrows]; either may be NULL; *nrows_out = nranks * V).  Synchronises. */
+int prv_get_gathered(prv_ctx* ctx, uint64_t* rows_out, uint32_t* ids_out, uint32_t* nrows_out);
 int prv_comm_destroy(prv_ctx* ctx);
 
 #ifdef __cplusplus

@@ -47,7 +47,8 @@ class Timing(C.Structure):
                 ("march_ms", C.c_float), ("march_launches", C.c_uint32), ("project_ms", C.c_float), ("project_launches", C.c_uint32),
                 ("count_ms", C.c_float), ("count_launches", C.c_uint32), ("greedy_ms", C.c_float), ("greedy_launches", C.c_uint32),
                 ("splat_ms", C.c_float), ("splat_launches", C.c_uint32), ("resolve_ms", C.c_float), ("resolve_launches", C.c_uint32),
-                ("other_ms", C.c_float), ("other_launches", C.c_uint32)]
+                ("other_ms", C.c_float), ("other_launches", C.c_uint32), ("gather_ms", C.c_float), ("gather_launches", C.c_uint32),
+                ("dropped", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -111,14 +112,16 @@ def lib():
         "prv_get_coverage_counts": (i, [vp, P(u32)]),
         "prv_get_hit_rank": (i, [vp, u32, u32, P(u32)]),
         "prv_get_depth": (i, [vp, u32, u32, P(f)]),
-        "prv_get_greedy": (i, [vp, P(u32), P(u32), P(u32), P(u64)]),
+        "prv_get_greedy": (i, [vp, P(u32), P(u32), u32, P(u32), P(u64)]),
+        "prv_greedy_path": (i, [vp]),
         "prv_get_cast_stats": (i, [vp, P(CastStats)]),
         "prv_cast_views": (i, [vp, P(d), P(d), u32, i, P(u64), P(u32), P(u32), P(f)]),
         "prv_precept": (i, [vp, P(d), P(d), vp, P(i)]),
-        "prv_greedy": (i, [vp, u32, u32, P(u32), P(u32), P(u32)]),
+        "prv_greedy": (i, [vp, u32, u32, P(u32), P(u32), u32, P(u32)]),
         "prv_set_cloud": (i, [vp, P(f), P(u8), u64]),
         "prv_render_views": (i, [vp, P(d), u32, i, P(u8), P(f)]),
         "prv_render_async": (i, [vp, u32, i]),
+        "prv_object_pixel_rate": (i, [vp, P(d), u32, i, P(d), P(u32)]),
         "prv_splat_focal": (f, [P(Intrinsics)]),
         "prv_score_ensemble": (i, [vp, P(u8), u32, u32, i, i, i, P(u8), P(d), P(C.c_int32)]),
         "prv_timing_reset": (i, [vp]),
@@ -132,6 +135,7 @@ def lib():
         "prv_comm_unique_id": (i, [vp]),
         "prv_comm_init": (i, [vp, vp, i, i]),
         "prv_allgather_bitsets_async": (i, [vp]),
+        "prv_get_gathered": (i, [vp, P(u64), P(u32), P(u32)]),
         "prv_comm_destroy": (i, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -269,6 +273,7 @@ class Context:
         if rc:
             raise PrvError(rc, lib().prv_last_error(None).decode())
         self.intr = None
+        self._greedy_max_iter = 0
 
     def close(self):
         if self._h:
@@ -350,6 +355,11 @@ class Context:
 
     def greedy_async(self, first_view, max_iter):
         self._chk(lib().prv_greedy_async(self._h, first_view, max_iter))
+        self._greedy_max_iter = int(max_iter)
+
+    @property
+    def greedy_path(self):
+        return lib().prv_greedy_path(self._h)
 
     def get_bitsets(self):
         out = np.zeros((self.num_views, self.words), dtype=np.uint64)
@@ -378,12 +388,15 @@ class Context:
         self._chk(lib().prv_get_depth(self._h, view_begin, view_count, _p(out, C.c_float)))
         return out
 
-    def get_greedy(self, max_iter, want_covered=True):
-        seq = np.zeros(max_iter + 1, dtype=np.uint32)
-        gains = np.zeros(max_iter + 1, dtype=np.uint32)
+    def get_greedy(self, max_iter=None, want_covered=True):
+        """Result of the last greedy_async.  The arrays are sized from the max_iter that call ran with (remembered here), not
+        from the caller's argument, which is only kept for source compatibility."""
+        cap = self._greedy_max_iter + 1
+        seq = np.zeros(cap, dtype=np.uint32)
+        gains = np.zeros(cap, dtype=np.uint32)
         n = C.c_uint32(0)
         cov = np.zeros(self.words, dtype=np.uint64) if want_covered else None
-        self._chk(lib().prv_get_greedy(self._h, _p(seq, C.c_uint32), _p(gains, C.c_uint32), C.byref(n), _p(cov, C.c_uint64)))
+        self._chk(lib().prv_get_greedy(self._h, _p(seq, C.c_uint32), _p(gains, C.c_uint32), cap, C.byref(n), _p(cov, C.c_uint64)))
         return seq[:n.value].copy(), gains[:n.value].copy(), cov
 
     def get_cast_stats(self):
@@ -432,7 +445,8 @@ class Context:
         seq = np.zeros(max_iter + 1, dtype=np.uint32)
         gains = np.zeros(max_iter + 1, dtype=np.uint32)
         n = C.c_uint32(0)
-        self._chk(lib().prv_greedy(self._h, first_view, max_iter, _p(seq, C.c_uint32), _p(gains, C.c_uint32), C.byref(n)))
+        self._chk(lib().prv_greedy(self._h, first_view, max_iter, _p(seq, C.c_uint32), _p(gains, C.c_uint32), max_iter + 1, C.byref(n)))
+        self._greedy_max_iter = int(max_iter)
         return seq[:n.value].copy(), gains[:n.value].copy()
 
     def set_cloud(self, xyz, rgb):
@@ -448,6 +462,14 @@ class Context:
         depth = np.zeros((V, H, W), dtype=np.float32) if want_depth else None
         self._chk(lib().prv_render_views(self._h, _p(pw, C.c_double), V, point_size, _p(rgba, C.c_uint8), _p(depth, C.c_float)))
         return rgba, depth
+
+    def object_pixel_rate(self, pose_world, point_size=5):
+        """prv_object_pixel_rate -> (mean non-white pixel fraction, per-view counts)."""
+        pw = np.ascontiguousarray(np.asarray(pose_world, dtype=np.float64).reshape(-1, 16))
+        rate = C.c_double(0)
+        counts = np.zeros(pw.shape[0], dtype=np.uint32)
+        self._chk(lib().prv_object_pixel_rate(self._h, _p(pw, C.c_double), pw.shape[0], point_size, C.byref(rate), _p(counts, C.c_uint32)))
+        return rate.value, counts
 
     def render_async(self, V, point_size=5):
         self._chk(lib().prv_render_async(self._h, V, point_size))
@@ -497,6 +519,15 @@ class Context:
     def comm_init(self, unique_id_bytes, rank, nranks):
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
         self._chk(lib().prv_comm_init(self._h, C.cast(buf, C.c_void_p), rank, nranks))
+
+    def get_gathered(self):
+        """(rows [nranks*V][words], view ids [nranks*V]) of the all-gathered coverage table."""
+        n = C.c_uint32(0)
+        self._chk(lib().prv_get_gathered(self._h, None, None, C.byref(n)))
+        rows = np.zeros((n.value, self.words), dtype=np.uint64)
+        ids = np.zeros(n.value, dtype=np.uint32)
+        self._chk(lib().prv_get_gathered(self._h, _p(rows, C.c_uint64), _p(ids, C.c_uint32), C.byref(n)))
+        return rows, ids
 
     def allgather_bitsets_async(self):
         self._chk(lib().prv_allgather_bitsets_async(self._h))

@@ -16,6 +16,24 @@ struct MapBuild {
     int cs;  // brick edge in voxels
 };
 
+// Leaf-order check and AABB of a key table, on the device (main.cpp:116-121: the table must be in begin_leafs() order, strictly
+// ascending Morton code).  out[0] = index of the first key whose code is not above its predecessor's (left at N when the
+// table is in order), out[1..3] = smallest key per axis, out[4..6] = largest.  The host initialises out to {N, 65535 x3, 0 x3}.
+// (Round 1 ran both loops on the host at the start of every prv_set_map while the GPU waited: 0.1 ms for 45 k keys.)
+__global__ void __launch_bounds__(256) map_check_kernel(const uint16_t* __restrict__ keys, uint32_t N, uint32_t* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const uint16_t k[3] = {keys[3 * (size_t)i], keys[3 * (size_t)i + 1], keys[3 * (size_t)i + 2]};
+    if (i > 0 && prv::morton_code(k[0], k[1], k[2]) <= prv::morton_code(keys[3 * (size_t)i - 3], keys[3 * (size_t)i - 2], keys[3 * (size_t)i - 1]))
+        atomicMin(out, i);
+    // thousands of keys fold into six words: test first (a stale read only costs a redundant atomic), as map_scatter_kernel does
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        if ((uint32_t)k[a] < __ldcg(out + 1 + a)) atomicMin(out + 1 + a, (uint32_t)k[a]);
+        if ((uint32_t)k[a] > __ldcg(out + 4 + a)) atomicMax(out + 4 + a, (uint32_t)k[a]);
+    }
+}
+
 // per occupied voxel: occupancy bit, padded-bitmap bit, and the (<= 8) coarse cells within one voxel of it
 __global__ void __launch_bounds__(256) map_scatter_kernel(MapBuild b) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,9 +149,12 @@ __global__ void __launch_bounds__(256) ingest_keys_kernel(const float* __restric
     uint16_t k[3];
     bool ok = true;
     for (int a = 0; a < 3; a++) {
-        const int scaled = (int)floor(prvk::dmul(resolution_factor, (double)xyz[3 * (size_t)i + a])) + prv::kTreeMaxVal;
-        ok = ok && scaled >= 0 && scaled < 2 * prv::kTreeMaxVal;
-        k[a] = (uint16_t)scaled;
+        // the range test is made on the double: (int) of a NaN / out-of-range double is 0 / saturated on the device but INT_MIN
+        // on x86 (where the reference, the oracle and prv_host_build_map then reject the point)
+        const double f = floor(prvk::dmul(resolution_factor, (double)xyz[3 * (size_t)i + a]));
+        const bool in_range = f >= -(double)prv::kTreeMaxVal && f < (double)prv::kTreeMaxVal;
+        ok = ok && in_range;
+        k[a] = in_range ? (uint16_t)((int)f + prv::kTreeMaxVal) : (uint16_t)0;
     }
     codes[i] = ok ? prv::morton_code(k[0], k[1], k[2]) : (1ull << 48);
     index[i] = i;

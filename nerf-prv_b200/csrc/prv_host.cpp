@@ -136,6 +136,7 @@ int prv_host_normalize_cloud(float* pts, uint64_t P, double target_size, double*
 int prv_host_build_map(const float* pts, const uint8_t* rgb, uint64_t P, double resolution, uint16_t* keys_out,
                        uint8_t* rgb_out, uint32_t* n_out) {
     if (!pts || !keys_out || !n_out || !(resolution > 0)) return PRV_ERR_INVALID;
+    try {
     const double rf = 1.0 / resolution;
     // (morton, point index): sorting groups points of one voxel with the first-inserted point first,
     // which is the voxel whose colour the reference keeps (main.cpp:1015-1021).
@@ -162,6 +163,9 @@ int prv_host_build_map(const float* pts, const uint8_t* rgb, uint64_t P, double 
         n++;
     }
     *n_out = n;
+    } catch (...) {  // std::bad_alloc of the sort buffer: nothing throws across the C ABI
+        return PRV_ERR_OOM;
+    }
     return PRV_OK;
 }
 

@@ -16,9 +16,11 @@ constexpr int kTreeMaxVal = 32768;
 
 // key = (int)floor(resolution_factor * coord) + 32768, valid when in [0, 65536)
 PRV_HD bool coord_to_key_checked(double coord, double resolution_factor, uint16_t& key) {
-    const int scaled = (int)floor(resolution_factor * coord) + kTreeMaxVal;
-    if (scaled < 0 || scaled >= 2 * kTreeMaxVal) return false;
-    key = (uint16_t)scaled;
+    // the range test is made on the double, so NaN and coordinates beyond the int range are rejected on every platform
+    // ((int) of such a double is INT_MIN on x86 -- rejected by the original test too -- but 0 / saturated in CUDA)
+    const double f = floor(resolution_factor * coord);
+    if (!(f >= -(double)kTreeMaxVal && f < (double)kTreeMaxVal)) return false;
+    key = (uint16_t)((int)f + kTreeMaxVal);
     return true;
 }
 

@@ -198,20 +198,11 @@ private:
             view.get_next_camera_pos(share_data->now_camera_pose_world, center);
             (share_data->now_camera_pose_world * view.pose.inverse()).toRowMajor(&pw[16 * i]);
         }
-        const int W = share_data->color_intrinsics.width, H = share_data->color_intrinsics.height;
-        std::vector<uint8_t> rgba((size_t)5 * W * H * 4);
+        // 5 renders and the non-white count stay on the device (main.cpp:913-931); only the counters come back
+        double r = -1;
         if (good && prv_set_camera(ctx, &share_data->color_intrinsics, 1.0) == PRV_OK && prv_set_cloud(ctx, pts.data(), rgb.data(), P) == PRV_OK &&
-            prv_render_views(ctx, pw.data(), 5, share_data->points_size_cloud, rgba.data(), nullptr) == PRV_OK) {
-            rate = 0;
-            for (int i = 0; i < 5; i++) {
-                size_t count = 0;
-                const uint8_t* img = rgba.data() + (size_t)i * W * H * 4;
-                for (size_t p = 0; p < (size_t)W * H; p++)
-                    if (img[4 * p] != 255 || img[4 * p + 1] != 255 || img[4 * p + 2] != 255) count++;
-                rate += (double)count / ((double)W * H);
-            }
-            rate /= 5;
-        }
+            prv_object_pixel_rate(ctx, pw.data(), 5, share_data->points_size_cloud, &r, nullptr) == PRV_OK)
+            rate = r;
         prv_destroy(ctx);
         return rate;
     }

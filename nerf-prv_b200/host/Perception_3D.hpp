@@ -117,7 +117,7 @@ public:
         seq.assign(max_iter + 1, 0);
         gains.assign(max_iter + 1, 0);
         uint32_t n = 0;
-        if (!ok || !check(prv_greedy(ctx, first_view, max_iter, seq.data(), gains.data(), &n))) return false;
+        if (!ok || !check(prv_greedy(ctx, first_view, max_iter, seq.data(), gains.data(), (uint32_t)seq.size(), &n))) return false;
         seq.resize(n);
         gains.resize(n);
         return true;

@@ -31,6 +31,16 @@ static inline uint32_t atomicOr(uint32_t* p, uint32_t v) {
     *p = old | v;
     return old;
 }
+static inline uint32_t atomicMin(uint32_t* p, uint32_t v) {
+    const uint32_t old = *p;
+    *p = std::min(old, v);
+    return old;
+}
+static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
+    const uint32_t old = *p;
+    *p = std::max(old, v);
+    return old;
+}
 template <typename T>
 static inline T __ldcg(const T* p) { return *p; }
 // the prefix kernels need warp shuffles and block barriers: never launched here (the prefix is a plain scan, done on the host)
@@ -90,6 +100,20 @@ int mkh_check_map_kernels(const uint16_t* keys, uint32_t N, double resolution, i
     b.leaf_of_raster = leaf_of_raster.data();
     b.keys = hm.keys.data();
     b.cs = brick_cs;
+    {   // map_check_kernel: leaf order + AABB of the key table (prv_set_map's validation)
+        uint32_t chk[7] = {N, 65535u, 65535u, 65535u, 0u, 0u, 0u};
+        launch(dim3((N + 255) / 256), dim3(256), [&] { map_check_kernel(hm.keys.data(), N, chk); });
+        if (chk[0] != N) return 6;
+        for (int a = 0; a < 3; a++)
+            if ((int)chk[1 + a] != m.lo[a] || (int)chk[4 + a] != m.lo[a] + m.n[a] - 1) return 7;
+        if (N >= 3) {  // a swapped pair must be reported at the index of the first key that is not above its predecessor
+            std::vector<uint16_t> bad(hm.keys);
+            for (int a = 0; a < 3; a++) std::swap(bad[3 * (size_t)(N / 2) + a], bad[3 * (size_t)(N / 2 + 1) + a]);
+            uint32_t chk2[7] = {N, 65535u, 65535u, 65535u, 0u, 0u, 0u};
+            launch(dim3((N + 255) / 256), dim3(256), [&] { map_check_kernel(bad.data(), N, chk2); });
+            if (chk2[0] != N / 2 + 1) return 8;
+        }
+    }
     launch(dim3((N + 255) / 256), dim3(256), [&] { map_scatter_kernel(b); });
     const size_t pad_rows = (size_t)(m.n[1] + 2) * (m.n[2] + 2);
     launch(dim3((unsigned)((pad_rows + 255) / 256)), dim3(256), [&] { map_shell_kernel(b); });

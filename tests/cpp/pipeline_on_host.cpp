@@ -16,7 +16,7 @@
 // splat_resolve_kernel's tile is dynamic shared memory (extern __shared__): here an ordinary global of the largest tile size
 #undef __shared__
 #define __shared__
-unsigned long long s_tile[(32 + 31) * (8 + 31)];
+unsigned long long s_tile[(32 + 31 + 32) * (8 + 31)];  // tile + row minima
 static inline uint32_t __float_as_uint(float f) {
     uint32_t u;
     std::memcpy(&u, &f, 4);

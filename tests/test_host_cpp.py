@@ -301,3 +301,75 @@ def test_yaml_values_equal_what_opencv_filestorage_reads(host_check, tmp_path, s
             else:
                 assert float(r[name]) == float(node.real()), (path, key)
         fs.release()
+
+
+@pytest.mark.gpu
+def test_size_augmentation_probe_without_size_txt(tmp_path, prv, orc, synth):
+    """SURVEY 8(f) #4 / main.cpp:851-964: without size.txt the labeler draws sizes in [last, 0.115) with the C library's
+    rand() until the object fills more than object_pixel_rate of 5 test renders (<= 6 draws), and writes the accepted size
+    (or -1).  The driver runs here with a pinned seed; the draws are recomputed with the same libc, the object rate of every
+    draw with the ORACLE's splat (the device side is prv_object_pixel_rate: render + non-white count without a read-back),
+    and the chosen size, the printed rates and the C-ABI counts must agree."""
+    import ctypes
+    W, H = 160, 120
+    cfg = write_env(tmp_path, synth, w=W, h=H, nviews=32, vmax=3)
+    raw = synth.raw_surface("torus", 78, 5000)
+    lat, rgb = synth.lattice_cloud(raw)
+    write_ply(tmp_path / "models" / "ShapeNet" / "obj_b.ply", lat, rgb, True)
+    gt = tmp_path / "out" / "Coverage_images" / "ShapeNet" / "obj_b"
+    drv = os.path.join(ROOT, "nerf-prv_b200", "prv_simulation")
+    seed = 4242
+    r = subprocess.run([drv, str(cfg), "--no-coverage"], input="3\nobj_b\n-1\n", capture_output=True, text=True, env=dict(os.environ, PRV_SIM_SEED=str(seed)))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (gt / "size.txt").exists(), r.stdout
+    chosen = float((gt / "size.txt").read_text())
+    printed_sizes = [float(l.split()[-1]) for l in r.stdout.splitlines() if l.startswith("random size is")]
+    printed_rates = [float(l.split()[-1]) for l in r.stdout.splitlines() if l.startswith("now object rate is")]
+    assert 1 <= len(printed_sizes) == len(printed_rates) <= 6
+
+    # the same draws with the same libc (View_Space.hpp:32-38 get_random_coordinate; RAND_MAX = 2^31 - 1 in glibc)
+    libc = ctypes.CDLL(None)
+    libc.srand(seed)
+    RAND_MAX = 2147483647
+
+    def draw(lo, hi):
+        x = libc.rand() * (RAND_MAX + 1) + libc.rand()
+        field = RAND_MAX * RAND_MAX + 2 * RAND_MAX
+        return float(x) / float(field) * (hi - lo) + lo
+
+    rate_threshold = float([l for l in open(cfg) if "object_pixel_rate" in l][0].split(":")[1])
+    intr = synth.intrinsics_for(prv.make_intrinsics, W, H)
+    oit = orc.make_intrinsics(intr.width, intr.height, intr.fx, intr.fy, intr.ppx, intr.ppy, intr.model, list(intr.coeffs))
+    sphere5 = synth.hemisphere_set(5)
+    ctx = prv.Context(0)
+    size, expected, tests = 0.075, None, 0
+    while True:
+        size = draw(size, 0.115)
+        assert abs(size - printed_sizes[tests]) <= 1e-6 * size  # (stdout prints 6 significant digits)
+        cloud, _ = orc.normalize_cloud(lat, size)
+        center = cloud.astype(np.float64).mean(axis=0)
+        center = np.array([np.sum(cloud[:, a].astype(np.float64)) / len(cloud) for a in range(3)])
+        init = sphere5 / np.linalg.norm(sphere5, axis=1, keepdims=True) * 0.3 + center
+        pw = prv.view_poses(init, center)
+        rate = 0.0
+        counts = []
+        for v in range(5):
+            rgba, _, _ = orc.splat(cloud, rgb, oit, pw[v], 5)
+            nonwhite = int(np.any(rgba[..., :3] != 255, axis=2).sum())
+            counts.append(nonwhite)
+            rate += nonwhite / float(W * H)
+        rate /= 5
+        ctx.set_camera(intr, 1.0)
+        ctx.set_cloud(cloud, rgb)
+        g_rate, g_counts = ctx.object_pixel_rate(pw, 5)
+        assert g_counts.tolist() == counts and g_rate == rate, (tests, g_counts.tolist(), counts)
+        assert abs(rate - printed_rates[tests]) <= 1e-5 * max(rate, 1e-9)
+        tests += 1
+        if not (rate <= rate_threshold and tests <= 5):
+            expected = size if tests <= 5 else -1.0
+            break
+    ctx.close()
+    assert tests == len(printed_sizes)
+    assert abs(chosen - expected) <= 1e-6 * abs(expected), (chosen, expected)
+    if expected > 0:
+        assert (gt / "3.json").exists()  # the driver went on to generate the view sets with that size

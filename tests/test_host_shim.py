@@ -8,7 +8,7 @@ import numpy as np
 
 def test_abi_exports_every_declared_symbol(prv):
     L = prv.lib()
-    assert L.prv_abi_version() == 1
+    assert L.prv_abi_version() == 2
     out = subprocess.run(["nm", "-D", prv.LIB_PATH], capture_output=True, text=True).stdout
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     declared = prv.declared_symbols()
