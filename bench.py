@@ -160,7 +160,7 @@ def _config(name, w, args, world, strong, l2_note):
             "height": w["H"], "voxels": int(len(w["keys"])), "resolution_m": w["resolution"], "l2": l2_note,
             "sharding": ("views interleaved over %d ranks + NCCL all-gather of the coverage rows in the timed step" % world) if strong else
                         ("one object per rank, no collective" if world > 1 else "single GPU"),
-            "variant": args.variant, "brick": args.brick, "brick_entry": bool(args.brick_entry)}
+            "variant": args.variant, "brick": args.brick, "brick_entry": bool(args.brick_entry), "stage_smem": bool(args.stage_smem), "stage_l2": bool(args.stage_l2)}
 
 
 def run_reference(args):
@@ -210,6 +210,7 @@ class Runner:
         ctx = self.ctx = prv.Context(local)
         ctx.set_variant(args.variant)
         ctx.set_brick_cull(args.brick, bool(args.brick_entry))  # tuning only: results are identical for every setting (include/prv.h)
+        ctx.set_staging(bool(args.stage_smem), bool(args.stage_l2))
         ctx.set_map(w["keys"], w["map_rgb"], w["resolution"])
         ctx.set_camera(w["intr"], 1.0)
         V = self.V = w["n_views"]
@@ -586,6 +587,8 @@ def main():
     ap.add_argument("--variant", type=int, default=2)
     ap.add_argument("--brick", type=int, default=8, choices=[4, 8, 16], help="prv_set_brick_cull: brick edge of the conservative cull in voxels")
     ap.add_argument("--brick-entry", type=int, default=1, choices=[0, 1], help="prv_set_brick_cull: start the exact march at the first set brick")
+    ap.add_argument("--stage-smem", type=int, default=1, choices=[0, 1], help="A/B: padded bitmap staged in the march blocks' shared memory")
+    ap.add_argument("--stage-l2", type=int, default=0, choices=[0, 1], help="A/B: L2 persisting window over the padded bitmap")
     ap.add_argument("--ref-seconds", type=float, default=6.0, help="reference arm: CPU seconds per step (sets the views sampled per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="N = 1: skip the C2 / C5 sub-measurements")

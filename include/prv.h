@@ -120,6 +120,12 @@ int         prv_set_variant(prv_ctx* ctx, int variant);
  * identical for every setting; only the probes_in / marched counters of prv_cast_stats move.
  * Takes effect at the next prv_set_map / prv_set_map_from_cloud. */
 int         prv_set_brick_cull(prv_ctx* ctx, int cell, int enter_at_brick);
+/* Where the occupancy bitmap is staged for the exact march (results identical).  bitmap_in_shared_memory (default on): the
+ * shell-padded bitmap is copied into every march block's shared memory when it is at most 44 KB (the 0.002 m maps: -1.7 % march
+ * time on C3); larger maps are read through the read-only L1 path.  l2_persisting_window (default off: measured no effect, the
+ * map is L2-resident anyway): an L2 persisting access-policy window over the bitmap, taking effect at the next prv_set_map.
+ * Numbers: profiles/r2_staging_ab.md. */
+int         prv_set_staging(prv_ctx* ctx, int bitmap_in_shared_memory, int l2_persisting_window);
 
 /* ---------------------------------------------------------------- host-side logic (pure host, no device)
  * One implementation of the reference's pose / view-space / map-insertion arithmetic for every caller. */

@@ -90,6 +90,7 @@ def lib():
         "prv_sync": (i, [vp]),
         "prv_set_variant": (i, [vp, i]),
         "prv_set_brick_cull": (i, [vp, i, i]),
+        "prv_set_staging": (i, [vp, i, i]),
         "prv_host_mat4_inverse": (i, [P(d), P(d)]),
         "prv_host_view_pose": (i, [P(d), P(d), P(d), P(d)]),
         "prv_host_view_pose_world": (i, [P(d), P(d), P(d)]),
@@ -305,6 +306,9 @@ class Context:
         """Brick edge of the conservative cull (4, 8 or 16 voxels) and whether the exact march starts at the first set
         brick.  Applies to the next set_map; results are identical for every setting."""
         self._chk(lib().prv_set_brick_cull(self._h, cell, 1 if enter_at_brick else 0))
+
+    def set_staging(self, bitmap_in_shared_memory=False, l2_persisting_window=False):
+        self._chk(lib().prv_set_staging(self._h, 1 if bitmap_in_shared_memory else 0, 1 if l2_persisting_window else 0))
 
     def set_map(self, keys, rgb, resolution):
         k = np.ascontiguousarray(keys, dtype=np.uint16)

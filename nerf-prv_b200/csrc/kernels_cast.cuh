@@ -62,8 +62,8 @@ __device__ __forceinline__ void write_hit(const CastParams& p, const ViewConst& 
 }
 
 // ---- AXIS pipeline ------------------------------------------------------------------------------------------------
-// kernel 1 (cull_kernel):   every pixel, loose float slab test against the grown AABB; survivors -> queue 1
-// kernel 2 (coarse_kernel): dense warps over queue 1, conservative coarse-brick walk; survivors -> queue 2
+// kernel 1 (cull_kernel):   every 32x32-pixel region against the AABB; dismissed regions are filled with "no hit", the rest -> region queue
+// kernel 2 (coarse_kernel): every pixel of the queued regions, conservative slab test + coarse-brick walk; survivors -> queue 2
 // kernel 3 (march_kernel):  dense warps over queue 2, the exact castRay march
 // Kernels 2 and 3 are persistent: kernel 2's blocks pull 256-ray chunks, kernel 3's warps 32-ray chunks of a flattened
 // (view, chunk) list with an atomic ticket, so expensive and cheap chunks balance across the 148 SMs and there is no
@@ -117,19 +117,19 @@ __device__ __forceinline__ void block_append2(bool keep, uint32_t v1, uint32_t v
 // One block per kCullRegions consecutive 32x32-pixel regions of one row of one view (blockIdx = (region group, region
 // row, view)): the view constants are fetched once and the region tests of the group run side by side (one warp each),
 // so the ~1.5 us of serial latency at the start of a block (constants from L2, barrier, region test) is paid once per
-// group instead of once per region (ncu had half of all stall samples there).  In a region every thread owns 4 pixels,
-// one in each 32x8 row-tile (a warp covers an 8x4 patch per row-tile).
+// group instead of once per region (ncu had half of all stall samples there).
 // Region test: the region's rays lie inside the pyramid spanned by the four corner rays taken 2 px outside the region
 // (the pixel->direction map is affine up to the lens distortion, whose deviation inside any region was verified on the
 // host to stay within that margin).  If all eight corners of the AABB grown by 2 voxels lie outside one side plane of the
 // pyramid, no ray of the region can touch the AABB: its pixels get "no hit" with 128-bit stores and nothing else.
+// Every other region is appended to the view's REGION queue: its pixels are the coarse kernel's work.  (Round 1 ran a float
+// slab test per pixel here and queued the surviving pixels; the coarse kernel then recomputed the direction and a tighter slab
+// test for each of them -- on C3 three quarters of this kernel's instructions were that duplicate per-pixel work, for a test
+// that removed 20 % of the rays it looked at.)
 constexpr int kCullRegions = 4;
 template <bool MASKED>
 __global__ void __launch_bounds__(256, 8) cull_kernel(const CastParams p) {
     __shared__ ViewConst s_vc;  // cull prefix only
-    __shared__ uint32_t s_woff[4][8];
-    __shared__ uint32_t s_base;
-    __shared__ uint32_t s_rays[8];
     __shared__ int s_skip[kCullRegions];
     const uint32_t view = blockIdx.z + p.view_base;
     load_view_prefix(s_vc, p.views + view);
@@ -149,7 +149,15 @@ __global__ void __launch_bounds__(256, 8) cull_kernel(const CastParams p) {
             const uint32_t bal = __ballot_sync(0xFFFFFFFFu, outside);
             skip = region_skip_from_ballot(bal);
         }
-        if (lane == 0) s_skip[warp] = skip ? 1 : 0;
+        if (lane == 0) {
+            s_skip[warp] = skip ? 1 : 0;
+            // a live region of a live view goes to the coarse kernel (a dead view's pixels keep whatever the caller reads as
+            // "view out of map": nothing is cast, the tables are written below as no hit)
+            if (!skip && region_x < regions_x && view_ok) {
+                const uint32_t pos = atomicAdd(p.qcount + view, 1u);
+                p.queue[(size_t)view * p.rqueue_cap + pos] = ((uint32_t)region_y << 16) | (uint32_t)region_x;
+            }
+        }
     }
     __syncthreads();
     const bool vec_ok = ((p.GW & 3) == 0) && ((p.pix_stride & 3ull) == 0ull);
@@ -157,102 +165,43 @@ __global__ void __launch_bounds__(256, 8) cull_kernel(const CastParams p) {
     for (int r = 0; r < kCullRegions; r++) {
         const int region_x = rx0 + r;
         if (region_x >= regions_x) break;  // uniform
-        if (s_skip[r] != 0) {
-            // the whole region provably misses: record "no hit" for its pixels (no compaction protocol)
-            if (p.pix_hit) {
-                if (vec_ok) {  // thread -> row t/8, 4 consecutive pixels: one 128-bit store per array
-                    const int px = (region_x << 5) + ((threadIdx.x & 7) << 2), py = (region_y << 5) + (threadIdx.x >> 3);
+        if (s_skip[r] == 0 && view_ok) continue;  // queued
+        // the whole region provably misses (or the view casts nothing): record "no hit" for its pixels
+        if (p.pix_hit && !MASKED) {
+            if (vec_ok) {  // thread -> row t/8, 4 consecutive pixels: one 128-bit store per array
+                const int px = (region_x << 5) + ((threadIdx.x & 7) << 2), py = (region_y << 5) + (threadIdx.x >> 3);
+                if (px < p.GW && py < p.GH) {
+                    const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
+                    *reinterpret_cast<uint4*>(p.pix_hit + o) = make_uint4(kNone, kNone, kNone, kNone);
+                    if (p.pix_depth) *reinterpret_cast<float4*>(p.pix_depth + o) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                }
+            } else {
+                const int px = (region_x << 5) + ((warp & 3) << 3) + (lane & 7);
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
                     if (px < p.GW && py < p.GH) {
                         const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
-                        *reinterpret_cast<uint4*>(p.pix_hit + o) = make_uint4(kNone, kNone, kNone, kNone);
-                        if (p.pix_depth) *reinterpret_cast<float4*>(p.pix_depth + o) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    }
-                } else {
-                    const int px = (region_x << 5) + ((warp & 3) << 3) + (lane & 7);
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
-                        if (px < p.GW && py < p.GH) {
-                            const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
-                            p.pix_hit[o] = kNone;
-                            if (p.pix_depth) p.pix_depth[o] = 0.0f;
-                        }
+                        p.pix_hit[o] = kNone;
+                        if (p.pix_depth) p.pix_depth[o] = 0.0f;
                     }
                 }
             }
-            skipped_rays += (uint32_t)(min(32, p.GW - (region_x << 5)) * min(32, p.GH - (region_y << 5)));
-            continue;
         }
-        uint32_t keep_mask = 0;  // bit t: this thread's pixel in row-tile t survives
-        uint32_t pids[4];
-        uint32_t nrays = 0;
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int px = (region_x << 5) + ((warp & 3) << 3) + (lane & 7);
-            const int py = (region_y << 5) + (t << 3) + ((warp >> 2) << 2) + (lane >> 3);
-            const bool in_grid = px < p.GW && py < p.GH;
-            const unsigned long long pid = (unsigned long long)py * p.GW + px;
-            pids[t] = ((uint32_t)py << 16) | (uint32_t)px;  // queues carry (y,x) packed: no division downstream
-            bool active = in_grid && view_ok;
-            if (MASKED && active) {
-                const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(pid >> 5));
-                active = (w >> (pid & 31)) & 1u;
-            }
-            bool survive = false;
-            if (active) {
-                if (!fast) {
-                    survive = true;  // this view needs the literal march (max-range test): no cull
-                } else {
-                    float dx, dy, dz;
-                    ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
-                    survive = !loose_miss(p.map, vc, dx, dy, dz);
-                }
-            }
-            if (in_grid && !survive && p.pix_hit && (!MASKED || active)) {
-                p.pix_hit[(size_t)view * p.pix_stride + pid] = kNone;
-                if (p.pix_depth) p.pix_depth[(size_t)view * p.pix_stride + pid] = 0.0f;
-            }
-            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, survive);
-            nrays += __popc(__ballot_sync(0xFFFFFFFFu, active));
-            if (survive) keep_mask |= 1u << t;
-            if (lane == 0) s_woff[t][warp] = __popc(bal);
-            // lane-local rank within the warp for this row-tile, kept in the high bits
-            keep_mask |= (uint32_t)__popc(bal & ((1u << lane) - 1u)) << (8 + 6 * t);
-        }
-        if (lane == 0) s_rays[warp] = nrays;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t tot = 0, rays = 0;
-            for (int t = 0; t < 4; t++)
-                for (int w = 0; w < 8; w++) {
-                    const uint32_t c = s_woff[t][w];
-                    s_woff[t][w] = tot;
-                    tot += c;
-                }
-            for (int w = 0; w < 8; w++) rays += s_rays[w];
-            s_base = tot ? atomicAdd(p.qcount + view, tot) : 0u;
-            skipped_rays += rays;  // posted once per block, below
-        }
-        __syncthreads();
-        if (keep_mask & 0xFu) {
-            uint32_t* q = p.queue + (size_t)view * p.queue_cap + s_base;
-#pragma unroll
-            for (int t = 0; t < 4; t++)
-                if (keep_mask & (1u << t)) q[s_woff[t][warp] + ((keep_mask >> (8 + 6 * t)) & 63u)] = pids[t];
-        }
-        __syncthreads();  // s_woff / s_base / s_rays are reused by the next region
+        if (view_ok) skipped_rays += (uint32_t)(min(32, p.GW - (region_x << 5)) * min(32, p.GH - (region_y << 5)));
     }
     if (threadIdx.x == 0 && skipped_rays) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)skipped_rays);
 }
 
-// exclusive prefix of chunk counts (chunk rays each) over the views of this launch -> s_prefix[0..nviews]
-__device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint32_t nviews, uint32_t* s_prefix, uint32_t chunk) {
+// exclusive prefix of chunk counts over the views of this launch -> s_prefix[0..nviews]; a view has ceil(count / chunk) chunks,
+// or count * per_item chunks when per_item > 0 (the coarse kernel: 4 row-tiles of 256 pixels per queued region)
+__device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint32_t nviews, uint32_t* s_prefix, uint32_t chunk, uint32_t per_item = 0) {
     __shared__ uint32_t s_part[8];
     // each thread owns a contiguous run of views
     const uint32_t per = (nviews + blockDim.x - 1) / blockDim.x;
     const uint32_t b = threadIdx.x * per, e = min(nviews, b + per);
     uint32_t sum = 0;
-    for (uint32_t v = b; v < e; v++) sum += (counts[v] + chunk - 1u) / chunk;
+    for (uint32_t v = b; v < e; v++) sum += per_item ? counts[v] * per_item : (counts[v] + chunk - 1u) / chunk;
     // block exclusive scan of the per-thread sums
     uint32_t incl = sum;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -267,13 +216,15 @@ __device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint3
     uint32_t run = woff + incl - sum;
     for (uint32_t v = b; v < e; v++) {
         s_prefix[v] = run;
-        run += (counts[v] + chunk - 1u) / chunk;
+        run += per_item ? counts[v] * per_item : (counts[v] + chunk - 1u) / chunk;
     }
     if (threadIdx.x == blockDim.x - 1) s_prefix[nviews] = woff + incl;
     __syncthreads();
 }
 
-template <int MINB>
+// Persistent blocks over the (view, region row-tile) list: per pixel the approximate direction and the conservative brick walk
+// (coarse_miss; its own slab test against the AABB grown by one voxel is the first thing it does).  Survivors -> queue 2.
+template <int MINB, bool MASKED>
 __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
     __shared__ ViewConst s_vc;
     __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
@@ -281,10 +232,12 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
     __shared__ uint32_t s_base;
     __shared__ uint32_t s_ticket, s_vl;
     if (threadIdx.x == 0) s_vl = 0;
-    build_chunk_prefix(p.qcount + p.view_base, p.nviews, s_prefix, blockDim.x);
+    __shared__ uint32_t s_rays[8];
+    build_chunk_prefix(p.qcount + p.view_base, p.nviews, s_prefix, 256u, 4u);
     const uint32_t total = s_prefix[p.nviews];
     uint32_t cur_view = 0xFFFFFFFFu;
     uint32_t vl = 0;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (;;) {
         if (threadIdx.x == 0) {
             const uint32_t t = atomicAdd(p.tickets + 0, 1u);
@@ -306,15 +259,23 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
             cur_view = view;
         }
         const ViewConst& vc = s_vc;
-        const uint32_t count = p.qcount[view];
-        const uint32_t idx = (g - s_prefix[vl]) * 256u + threadIdx.x;
+        // chunk = one 32x8 row-tile of a queued region; a warp covers an 8x4 patch of it
+        const uint32_t c = g - s_prefix[vl];
+        const uint32_t region = p.queue[(size_t)view * p.rqueue_cap + (c >> 2)];
+        const int px = (int)((region & 0xFFFFu) << 5) + ((warp & 3) << 3) + (lane & 7);
+        const int py = (int)((region >> 16) << 5) + (int)((c & 3u) << 3) + ((warp >> 2) << 2) + (lane >> 3);
+        const uint32_t pid = ((uint32_t)py << 16) | (uint32_t)px;  // queues carry (y,x) packed: no division downstream
+        bool active = px < p.GW && py < p.GH;
+        if (MASKED && active) {
+            const unsigned long long lin = (unsigned long long)py * p.GW + px;
+            const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(lin >> 5));
+            active = (w >> (lin & 31)) & 1u;
+        }
         bool keep = false;
-        uint32_t pid = 0, cell = kNone;
-        if (idx < count) {
-            pid = p.queue[(size_t)view * p.queue_cap + idx];
-            const int py = (int)(pid >> 16), px = (int)(pid & 0xFFFFu);
+        uint32_t cell = kNone;
+        if (active) {
             if (!(vc.flags & kViewFastOk)) {
-                keep = true;
+                keep = true;  // this view needs the literal march (max-range test): no cull
             } else {
                 float dx, dy, dz;
                 ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
@@ -326,10 +287,17 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
                 if (p.pix_depth) p.pix_depth[o] = 0.0f;
             }
         }
+        const uint32_t nact = __popc(__ballot_sync(0xFFFFFFFFu, active));
+        if (lane == 0) s_rays[warp] = nact;
         if (p.queue2b)
             block_append2(keep, pid, cell, p.queue2 + (size_t)view * p.queue_cap, p.queue2b + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
         else
             block_append(keep, pid, p.queue2 + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
+        if (threadIdx.x == 0) {  // (block_append's barriers order the s_rays stores before, and its last one the reuse after)
+            uint32_t rays = 0;
+            for (int w = 0; w < 8; w++) rays += s_rays[w];
+            if (rays) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)rays);
+        }
     }
 }
 
@@ -338,12 +306,23 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
 // (with 64-ray block chunks ncu showed ~11 % of warp time parked at the ticket barrier waiting for the sibling warp).
 // The ticket for the NEXT chunk is requested before the current chunk is marched, so the ~1 us atomic round trip is
 // hidden (un-prefetched warp tickets had measured 6 % slower than block tickets).  Measured on C2: 56 registers / 32 warps
-// per SM (no spills) 0.514 ms, 48 / 40 (16 B spilled) 0.521 ms, 40 / 48 (88 B spilled) 0.530 ms.
+// per SM (no spills) 0.514 ms, 48 / 40 (16 B spilled) 0.521 ms, 40 / 48 (88 B spilled) 0.530 ms; round 2 (profiles/
+// r2_staging_ab.md): 9 blocks of 128 threads (36 warps, 56 registers, 16 B spilled) +1 %, two probes in flight instead of
+// four +2 % on C2 / -0.5 % on C3.
 constexpr int kMarchBlock = 256, kMarchMinBlocks = 4;
-template <int BS, int MINB>
+#ifndef PRVK_HOST_CHECK
+extern __shared__ uint32_t s_dyn_pad[];  // SMEM variant: the shell-padded occupancy bitmap, staged once per block
+#else
+static uint32_t* const s_dyn_pad = nullptr;  // (the CPU checker runs the default variant)
+#endif
+template <int BS, int MINB, bool SMEM = false>
 __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
     __shared__ ViewConst s_vcw[BS / 32];
     __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
+    if (SMEM) {
+        for (uint32_t i = threadIdx.x; i < p.map.pad_words; i += BS) s_dyn_pad[i] = __ldg(p.map.bitmap_pad + i);
+        // (build_chunk_prefix's barriers order these stores before the first probe)
+    }
     build_chunk_prefix(p.qcount2 + p.view_base, p.nviews, s_prefix, 32u);
     const uint32_t total = s_prefix[p.nviews];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -393,7 +372,7 @@ __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
                     march_plain(p.map, p.cam, vc, r, res);
                     break;
                 }
-                if (march_axis(p.map, vc, r, cell, res)) break;
+                if (march_axis<SMEM>(p.map, vc, r, cell, res, s_dyn_pad)) break;
                 cell = kNone;
             }
             write_hit(p, vc, view, pid, res);

@@ -3,7 +3,7 @@
 // Compiles the per-ray device code of the ray-cast kernels -- nerf-prv_b200/csrc/prv_kernels.cuh, unchanged -- with g++ and
 // runs it one ray at a time on the CPU, so the `-m "not gpu"` suite can hold the kernels' arithmetic and the exactness of
 // the three conservative culls against the oracle without a GPU:
-//   * region cull (region_corner_outside / region_skip_from_ballot), loose slab cull (ray_direction_approx + loose_miss)
+//   * region cull (region_corner_outside / region_skip_from_ballot), slab + brick cull (ray_direction_approx + coarse_miss)
 //     and coarse brick cull (coarse_miss) exactly as cull_kernel / coarse_kernel chain them;
 //   * the exact set-up (ray_direction + ray_init) and the three march variants (march_plain / march_fast / march_axis);
 //   * the per-view constants and the "fast path" proof (prv_view_const.hpp, the code prv_set_views runs);
@@ -115,6 +115,7 @@ bool build_map(HostMap& hm, const uint16_t* keys, const uint8_t* rgb, uint32_t N
     const size_t slack_bits = ((size_t)3 * (m.n[1] + 2) + 2) << row_log2;
     hm.pad.assign(((pad_rows << row_log2) + 2 * slack_bits) / 32, 0u);
     m.pad_row_log2 = row_log2;
+    m.pad_words = (uint32_t)hm.pad.size();
     m.pad_bit_offset = (uint32_t)slack_bits;
     auto set_pad = [&](int c0, int c1, int c2) {  // padded cell coordinates (0..n+1)
         const size_t L = slack_bits + (((size_t)c2 * (m.n[1] + 2) + c1) << row_log2) + (size_t)c0;
@@ -198,7 +199,7 @@ DevCam make_cam(const prv_intrinsics& it, double max_range, int force_region_cul
 
 enum { S_RAYS = 0, S_REGION_CULLED, S_LOOSE_CULLED, S_COARSE_CULLED, S_MARCHED, S_PROBES, S_STEPS, S_HITS, S_FLAGS, S_REGION_OK, S_BOX_ENTRIES, S_BOX_FALLBACKS, S_N };
 
-// one pixel through stages 1b..3 of the AXIS pipeline (cull_kernel's per-pixel part, coarse_kernel, march_kernel)
+// one pixel through stages 2..3 of the AXIS pipeline (coarse_kernel, march_kernel)
 void axis_pixel(const HostMap& hm, const DevCam& cam, const ViewConst& vc, int px, int py, CastResult& res, uint64_t* st, bool entry = true) {
     res.rank = kNone;
     res.steps = res.probes = 0;
@@ -208,10 +209,6 @@ void axis_pixel(const HostMap& hm, const DevCam& cam, const ViewConst& vc, int p
     if (fast) {
         float dx, dy, dz;
         ray_direction_approx(cam, vc, (float)px, (float)py, dx, dy, dz);
-        if (loose_miss(hm.m, vc, dx, dy, dz)) {
-            st[S_LOOSE_CULLED]++;
-            return;
-        }
         if (coarse_miss(hm.m, vc, dx, dy, dz, cell)) {
             st[S_COARSE_CULLED]++;
             return;

@@ -135,7 +135,7 @@ int poh_cast_views(const uint16_t* keys, const uint8_t* rgb, uint32_t N, double 
     p.GH = voxel ? cam.H + 1 : cam.H;
     p.pix_stride = (unsigned long long)p.GW * p.GH;
     const uint32_t words = hm.m.words64;
-    std::vector<uint32_t> bitsets32((size_t)V * words * 2, 0u), queue((size_t)V * p.pix_stride), queue2((size_t)V * p.pix_stride), qcount(2 * (size_t)V, 0u),
+    std::vector<uint32_t> bitsets32((size_t)V * words * 2, 0u), queue((size_t)V * (size_t)(((p.GW + 31) / 32) * ((p.GH + 31) / 32))), queue2((size_t)V * p.pix_stride), qcount(2 * (size_t)V, 0u),
         tickets(2, 0u), mask, voxel_pix;
     std::vector<unsigned long long> stats((size_t)V * 4, 0ull);
     std::vector<uint32_t> queue2b;
@@ -149,6 +149,7 @@ int poh_cast_views(const uint16_t* keys, const uint8_t* rgb, uint32_t N, double 
     p.queue2 = queue2.data();
     p.qcount2 = qcount.data() + V;
     p.queue_cap = p.pix_stride;
+    p.rqueue_cap = (uint32_t)(((p.GW + 31) / 32) * ((p.GH + 31) / 32));
     p.tickets = tickets.data();
     p.view_base = 0;
     p.nviews = V;
@@ -168,7 +169,10 @@ int poh_cast_views(const uint16_t* keys, const uint8_t* rgb, uint32_t N, double 
         simt_launch(rgrid, dim3(256), [&] { cull_kernel<true>(p); });
     else
         simt_launch(rgrid, dim3(256), [&] { cull_kernel<false>(p); });
-    simt_launch(dim3((unsigned)grid_blocks), dim3(256), [&] { coarse_kernel<8>(p); });
+    if (voxel)
+        simt_launch(dim3((unsigned)grid_blocks), dim3(256), [&] { coarse_kernel<8, true>(p); });
+    else
+        simt_launch(dim3((unsigned)grid_blocks), dim3(256), [&] { coarse_kernel<8, false>(p); });
     simt_launch(dim3((unsigned)grid_blocks), dim3(kMarchBlock), [&] { march_kernel<kMarchBlock, kMarchMinBlocks>(p); });
     if (voxel && voxel_hit_out)
         simt_launch(dim3((N + 255) / 256, V), dim3(256), [&] { gather_voxel_hits_kernel(N, voxel_pix.data(), pix_hit_out, p.pix_stride, voxel_hit_out); });
