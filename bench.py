@@ -158,7 +158,8 @@ def _workload_text(name, w):
 def _config(name, w, args, world, strong, l2_note):
     return {"workload": _workload_text(name, w), "objects_per_step": 1 if (strong or world == 1) else world, "views": w["n_views"], "width": w["W"],
             "height": w["H"], "voxels": int(len(w["keys"])), "resolution_m": w["resolution"], "l2": l2_note,
-            "sharding": ("views interleaved over %d ranks + NCCL all-gather of the coverage rows in the timed step" % world) if strong else
+            "sharding": ("views interleaved over %d ranks + all-gather of the coverage rows in the timed step (%s)" %
+                         (world, "peer-memory stores over NVLink fused into the count kernel" if args.gather == "p2p" else "ncclAllGather")) if strong else
                         ("one object per rank, no collective" if world > 1 else "single GPU"),
             "variant": args.variant, "brick": args.brick, "brick_entry": bool(args.brick_entry), "stage_smem": bool(args.stage_smem), "stage_l2": bool(args.stage_l2)}
 
@@ -225,10 +226,18 @@ class Runner:
             t = torch.tensor(list(uid), dtype=torch.uint8, device="cuda")
             dist.broadcast(t, 0)
             ctx.comm_init(bytes(t.cpu().tolist()), rank, world)
+            self.p2p = args.gather == "p2p"
+            if self.p2p:
+                # peer-memory exchange: every rank's arena handle to every rank, then rows travel as NVLink stores from the count kernel
+                handles = [None] * world
+                dist.all_gather_object(handles, ctx.p2p_export())
+                ctx.p2p_import(handles, rank, world)
             ctx.set_views(self.pose, self.init, view_ids=ids)
+            dist.barrier()
             self.local_views = int(real.sum())
         else:
             self.ids = None
+            self.p2p = False
             self.pose, self.init = np.ascontiguousarray(w["pose_world"]), np.ascontiguousarray(w["init_pos"])
             ctx.set_views(self.pose, self.init)
             self.local_views = V
@@ -240,7 +249,7 @@ class Runner:
         self.needs_flush = self.rays_local * 8 <= 2 * L2_BYTES
 
     def step(self):
-        self.ctx.cast_async(self.prv.MODE_DENSE, want_pixels=True)
+        self.ctx.cast_async(self.prv.MODE_DENSE, want_pixels=True, publish=self.p2p)
         if self.strong:
             self.ctx.allgather_bitsets_async()
         self.ctx.greedy_async(0, GREEDY_MAX_ITER)
@@ -320,7 +329,7 @@ class Runner:
                 ctx.cast_views(pw_h, ip_h, mode=prv.MODE_DENSE, want_bitsets=True, want_counts=True, out_bitsets=bits_h, out_counts=cnt_h)
             else:
                 ctx.set_views(pw_h, ip_h, view_ids=self.ids)
-                ctx.cast_async(prv.MODE_DENSE, False)
+                ctx.cast_async(prv.MODE_DENSE, False, publish=self.p2p)
                 ctx.allgather_bitsets_async()
                 ctx.get_bitsets()
                 ctx.get_coverage_counts()
@@ -589,6 +598,7 @@ def main():
     ap.add_argument("--brick-entry", type=int, default=1, choices=[0, 1], help="prv_set_brick_cull: start the exact march at the first set brick")
     ap.add_argument("--stage-smem", type=int, default=1, choices=[0, 1], help="A/B: padded bitmap staged in the march blocks' shared memory")
     ap.add_argument("--stage-l2", type=int, default=0, choices=[0, 1], help="A/B: L2 persisting window over the padded bitmap")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="N > 1: transport of the coverage-row all-gather")
     ap.add_argument("--ref-seconds", type=float, default=6.0, help="reference arm: CPU seconds per step (sets the views sampled per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="N = 1: skip the C2 / C5 sub-measurements")

@@ -178,7 +178,11 @@ uint32_t prv_num_views(const prv_ctx* ctx);
  * consumers of its coverage rows (prv_allgather_bitsets_async, prv_greedy_async) on the other, with the rows double-
  * buffered -- a caller that enqueues cast / [all-gather] / greedy for several steps back to back gets the scoring of step k
  * overlapped with the cull and march of step k+1.  Every prv_get_* / prv_sync / prv_event_record joins both streams. */
-int prv_cast_async(prv_ctx* ctx, int mode, int want_pixels /* also write per-pixel hit rank + depth */);
+#define PRV_CAST_PIXELS 1  /* also write the per-pixel hit rank + depth tables */
+#define PRV_CAST_PUBLISH 2 /* multi-GPU (after prv_comm_p2p_import): the coverage-count kernel also stores every row into every
+                              rank's gathered table over NVLink peer memory -- the send side of the all-gather fused into the
+                              kernel that reads the rows anyway; EVERY rank must then call prv_allgather_bitsets_async */
+int prv_cast_async(prv_ctx* ctx, int mode, int flags /* PRV_CAST_* */);
 int prv_greedy_async(prv_ctx* ctx, uint32_t first_view, uint32_t max_iter);
 
 /* ---------------------------------------------------------------- results (synchronise, then copy D2H) */
@@ -251,8 +255,16 @@ int prv_flush_l2(prv_ctx* ctx);
 int prv_comm_unique_id(void* id_out_128 /* ncclUniqueId bytes */);
 int prv_comm_init(prv_ctx* ctx, const void* id_128, int rank, int nranks);
 /* all-gathers the local coverage rows (equal V on every rank, view ids from prv_set_view_ids) so every rank
- * holds the full table; the greedy then runs replicated and deterministic on every rank. */
+ * holds the full table; the greedy then runs replicated and deterministic on every rank.  Transport: the peer-memory
+ * exchange when prv_comm_p2p_import has been called (stores over NVLink into every rank's table + release / acquire flags,
+ * no NCCL; fused into the count kernel by PRV_CAST_PUBLISH), else ncclAllGather (prv_comm_init). */
 int prv_allgather_bitsets_async(prv_ctx* ctx);
+/* Peer-memory exchange set-up (one process per GPU, all on one NVLink / NVSwitch box): every rank allocates its arena and
+ * exports a 64-byte cudaIpc handle; the caller exchanges the handles (torch.distributed, MPI, a file ...) and every rank
+ * imports all of them (handles = nranks x 64 bytes in rank order; its own slot is ignored).  table_bytes_max bounds
+ * nranks * V * (words * 8 + 4), the gathered table + ids of one step (0 = 16 MB; the 1024-view workload needs 1.8 MB). */
+int prv_comm_p2p_export(prv_ctx* ctx, void* handle_out_64, uint64_t table_bytes_max);
+int prv_comm_p2p_import(prv_ctx* ctx, const void* handles, int rank, int nranks);
 /* the table the replicated selection runs over after the all-gather: nranks * V rows in rank order and their view ids
  * (rows_out [nrows][words], ids_out [nrows]; either may be NULL; *nrows_out = nranks * V).  Synchronises. */
 int prv_get_gathered(prv_ctx* ctx, uint64_t* rows_out, uint32_t* ids_out, uint32_t* nrows_out);

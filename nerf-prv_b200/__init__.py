@@ -137,6 +137,8 @@ def lib():
         "prv_comm_init": (i, [vp, vp, i, i]),
         "prv_allgather_bitsets_async": (i, [vp]),
         "prv_get_gathered": (i, [vp, P(u64), P(u32), P(u32)]),
+        "prv_comm_p2p_export": (i, [vp, vp, u64]),
+        "prv_comm_p2p_import": (i, [vp, vp, i, i]),
         "prv_comm_destroy": (i, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -354,8 +356,9 @@ class Context:
     def num_views(self):
         return lib().prv_num_views(self._h)
 
-    def cast_async(self, mode=MODE_DENSE, want_pixels=False):
-        self._chk(lib().prv_cast_async(self._h, mode, 1 if want_pixels else 0))
+    def cast_async(self, mode=MODE_DENSE, want_pixels=False, publish=False):
+        """publish: PRV_CAST_PUBLISH (multi-GPU peer-memory exchange fused into the count kernel)."""
+        self._chk(lib().prv_cast_async(self._h, mode, (1 if want_pixels else 0) | (2 if publish else 0)))
 
     def greedy_async(self, first_view, max_iter):
         self._chk(lib().prv_greedy_async(self._h, first_view, max_iter))
@@ -523,6 +526,16 @@ class Context:
     def comm_init(self, unique_id_bytes, rank, nranks):
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
         self._chk(lib().prv_comm_init(self._h, C.cast(buf, C.c_void_p), rank, nranks))
+
+    def p2p_export(self, table_bytes_max=0):
+        h = (C.c_char * 64)()
+        self._chk(lib().prv_comm_p2p_export(self._h, h, table_bytes_max))
+        return bytes(h)
+
+    def p2p_import(self, handles, rank, nranks):
+        buf = b"".join(handles)
+        assert len(buf) == 64 * nranks
+        self._chk(lib().prv_comm_p2p_import(self._h, buf, rank, nranks))
 
     def get_gathered(self):
         """(rows [nranks*V][words], view ids [nranks*V]) of the all-gathered coverage table."""

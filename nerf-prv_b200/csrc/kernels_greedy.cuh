@@ -15,6 +15,74 @@ __global__ void __launch_bounds__(256) popcount_rows_kernel(const uint64_t* rows
     if (threadIdx.x == 0) counts[blockIdx.x] = t;
 }
 
+// Fused coverage count + all-gather send side (multi-GPU, views sharded): the pass that reads every local coverage row once
+// to count it also STORES the row into the gathered table of every rank -- peer memory mapped over NVLink (cudaIpc), 128-bit
+// stores -- together with the view id, and the last block to finish publishes the step number in every rank's flag word.  No
+// NCCL call, no extra read of the rows, no host involvement.  PeerArena describes one rank's arena (same layout everywhere):
+//   flags[kMaxPeers] u32 (flag[r] = last step rank r has published here) | error u32 | 4 x { rows [G*V][words] u64, ids [G*V] u32 }
+// A step uses buffer step % 4: a rank can run at most three published casts ahead of the slowest reader of its stores (each
+// cast waits for the rank's own selection two steps back, which waited for everybody's publication of that step), so four
+// buffers are never overwritten while read.
+#ifndef PRVK_HOST_CHECK  // (system-scope PTX: device only)
+constexpr int kMaxPeers = 8;
+constexpr uint32_t kPeerBuffers = 4;
+struct PeerArena {
+    uint32_t* flags[kMaxPeers];
+    uint64_t* rows[kMaxPeers];  // buffer (step % 4) of each rank's arena
+    uint32_t* ids[kMaxPeers];
+    uint32_t nranks, rank;
+};
+__global__ void __launch_bounds__(256) count_publish_kernel(const uint64_t* __restrict__ rows, uint32_t words64, uint32_t V, uint32_t* __restrict__ counts,
+                                                            const uint32_t* __restrict__ view_ids, PeerArena pa, uint32_t step, uint32_t* done) {
+    __shared__ uint32_t s_red[8];
+    __shared__ uint32_t s_last;
+    const uint32_t v = blockIdx.x;
+    const ulonglong2* row = reinterpret_cast<const ulonglong2*>(rows + (size_t)v * words64);
+    const size_t slot = (size_t)pa.rank * V + v;
+    uint32_t c = 0;
+    for (uint32_t w = threadIdx.x; w < words64 / 2; w += blockDim.x) {
+        const ulonglong2 x = row[w];
+        c += __popcll(x.x) + __popcll(x.y);
+        for (uint32_t r = 0; r < pa.nranks; r++) reinterpret_cast<ulonglong2*>(pa.rows[r] + slot * words64)[w] = x;  // local + 7 NVLink stores
+    }
+    if (threadIdx.x < pa.nranks) pa.ids[threadIdx.x][slot] = view_ids[v];
+    const uint32_t t = block_reduce_sum(c, s_red);
+    __threadfence_system();  // this block's peer stores are visible system-wide before it is counted as done
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        counts[v] = t;
+        s_last = atomicAdd(done, 1u) == V - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {  // every block's stores have been fenced: publish the step (release) in every rank's arena
+        if (threadIdx.x == 0) *done = 0;
+        __threadfence_system();
+        if (threadIdx.x < pa.nranks) {
+            uint32_t* f = pa.flags[threadIdx.x] + pa.rank;
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(step) : "memory");
+        }
+    }
+}
+
+// all-gather receive side: wait until every rank has published `step` here (one lane per rank, acquire loads), then the
+// selection may read the table.  A rank that never shows up is reported after ~20 s instead of hanging the GPU.
+__global__ void __launch_bounds__(32) wait_published_kernel(const uint32_t* flags, uint32_t nranks, uint32_t step, uint32_t* error) {
+    const uint32_t r = threadIdx.x;
+    if (r >= nranks) return;
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t f;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(f) : "l"(flags + r) : "memory");
+        if ((int32_t)(f - step) >= 0) break;
+        if (clock64() - t0 > 40000000000ll) {  // ~20 s
+            atomicExch(error, 1u + r);
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+#endif
+
 // greedy set cover ---------------------------------------------------------------------------------
 // best[k] = max over views of (gain << 32) | (0xFFFFFFFF - view_id): largest gain, then LOWEST view id.
 __global__ void __launch_bounds__(256) greedy_init_kernel(const uint64_t* rows, uint32_t words64, uint32_t first_row, uint32_t first_id,

@@ -22,12 +22,16 @@ def _gpus():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("gather", ["p2p", "nccl"])
 @pytest.mark.parametrize("n", [2, 4, 8])
-def test_view_sharded_c3_matches_the_oracle_on_every_rank(n):
+def test_view_sharded_c3_matches_the_oracle_on_every_rank(n, gather):
+    """gather = p2p: rows stored into every rank's table over NVLink peer memory by the count kernel (PRV_CAST_PUBLISH), flags
+    with release / acquire; gather = nccl: ncclAllGather on the scoring stream."""
     if _gpus() < n:
         pytest.skip("needs %d GPUs" % n)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1", "--master-port",
-           str(29700 + n), os.path.join(ROOT, "bench.py"), "--gpus", str(n), "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-sustained"]
+           str(29700 + n + (10 if gather == "nccl" else 0)), os.path.join(ROOT, "bench.py"), "--gpus", str(n), "--steps", "3", "--warmup", "3",
+           "--no-cpu-baseline", "--no-sustained", "--gather", gather]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
@@ -39,4 +43,5 @@ def test_view_sharded_c3_matches_the_oracle_on_every_rank(n):
     golden = json.load(open(os.path.join(ROOT, "tests", "golden", "golden_c3.json")))["cases"][0]
     assert d["greedy_seq"] == golden["greedy_seq"]
     assert len(d["per_rank"]) == n and all(r_["allgather_ms"] > 0 for r_ in d["per_rank"])
+    assert ("peer-memory" in d["config"]["sharding"]) == (gather == "p2p")
     assert sum(r_["local_views"] for r_ in d["per_rank"]) == 1024
