@@ -533,6 +533,27 @@ def measure_c5_splat(prv, synth, args, local):
                                "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak}}
 
 
+def measure_ensemble(prv, local):
+    """SURVEY 8(f) #2, the reference's live "candidate views scored" loop (nbv_loop cases 2 / 3, main.cpp:2039-2161): per-pixel
+    variance over the ensemble renders at W/16 x H/16, summed per view in the reference's order, arg-max.  Host-buffer API:
+    the images travel H2D inside the timed call (as they would from instant-ngp's output), the scores come back."""
+    rng = np.random.default_rng(5)
+    V, E, W, H = 100, 2, 80, 45  # 100 candidate views, ensemble_num 2 (Share_Data.hpp:505-507), 1280x720 / 16 (main.cpp:1796-1806)
+    images = rng.integers(0, 256, size=(V, E, H, W, 4), dtype=np.uint8)
+    ctx = prv.Context(local)
+    out = {"views": V, "ensemble_num": E, "width": W, "height": H}
+    for method in (2, 3):
+        ctx.score_ensemble(images, method)
+        n = 50
+        t0 = time.perf_counter()
+        for _ in range(n):
+            best, scores = ctx.score_ensemble(images, method)
+        dt = (time.perf_counter() - t0) / n
+        out["method_%d" % method] = {"ms_per_call": dt * 1e3, "views_scored_per_sec": V / dt, "h2d_bytes_per_call": int(images.nbytes), "best_view": int(best)}
+    ctx.close()
+    return out
+
+
 def run_own(args):
     rank, world, local = _dist_env()
     import load_pkg
@@ -554,6 +575,7 @@ def run_own(args):
             line["c2"] = {k: c2[k] for k in ("value", "unit", "steps", "ms_per_step", "config", "e2e", "roofline", "roofline_greedy", "kernel_ms_per_step",
                                              "cast_stats", "views_scored_per_sec", "greedy_len", "coverage_rate")}
         line["c5_splat"] = measure_c5_splat(prv, synth, args, local)
+        line["ensemble_scoring"] = measure_ensemble(prv, local)
         if not args.no_cpu_baseline:
             # the reference's own execution structure (one std::thread per voxel in batches of
             # num_of_thread = 20, pose inverse per voxel, sparse lookup; main.cpp:124-130, 238-284) on one view of C1

@@ -44,7 +44,7 @@ typedef enum prv_status {
     PRV_ERR_NO_DEVICE = -2,   /* no CUDA device / wrong architecture             */
     PRV_ERR_CUDA = -3,        /* CUDA runtime error (see prv_last_error)         */
     PRV_ERR_OOM = -4,         /* host or device allocation failed                */
-    PRV_ERR_UNSUPPORTED = -5, /* e.g. distortion models 3/5 (transcendental)     */
+    PRV_ERR_UNSUPPORTED = -5, /* e.g. deprojecting distortion model 1, maps too large for the dense bitmap */
     PRV_ERR_NCCL = -6,        /* NCCL not loadable / collective failed           */
     PRV_ERR_IO = -7           /* file output failed                              */
 } prv_status;
@@ -146,6 +146,12 @@ int prv_host_normalize_cloud(float* pts_xyz, uint64_t P, double target_size, dou
  * keys_out/rgb_out need room for P entries; *n_out = full_voxels. */
 int prv_host_build_map(const float* pts_xyz, const uint8_t* rgb, uint64_t P, double resolution,
                        uint16_t* keys_out, uint8_t* rgb_out, uint32_t* n_out);
+
+/* rs2_project_point_to_pixel / rs2_deproject_pixel_to_point (Share_Data.hpp:92-137, 140-196), all six distortion models, float
+ * arithmetic in the reference's order; tan / atan of models 3 and 5 are this host's float libm, as in the reference built on
+ * this host.  The library itself uses them for those two models (per-pixel deprojection table, host-side voxel projection). */
+int prv_host_project_point_to_pixel(const prv_intrinsics* intr, const float point[3], float pixel_out[2]);
+int prv_host_deproject_pixel_to_point(const prv_intrinsics* intr, const float pixel[2], float depth, float point_out[3]);
 
 /* Leaf-order check of a key table: keys must be in strictly ascending begin_leafs() (Morton) order, as prv_set_map requires
  * (main.cpp:116-121).  *first_bad_out = index of the first key that is not above its predecessor, or N when the table is in

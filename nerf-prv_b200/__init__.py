@@ -97,6 +97,8 @@ def lib():
         "prv_host_view_space": (i, [P(f), u64, P(d), i, d, d, P(d), P(d), P(d), P(i)]),
         "prv_host_normalize_cloud": (i, [P(f), u64, d, P(d)]),
         "prv_host_build_map": (i, [P(f), P(u8), u64, d, P(u16), P(u8), P(u32)]),
+        "prv_host_project_point_to_pixel": (i, [P(Intrinsics), P(f), P(f)]),
+        "prv_host_deproject_pixel_to_point": (i, [P(Intrinsics), P(f), f, P(f)]),
         "prv_host_check_leaf_order": (i, [P(u16), u32, P(u32)]),
         "prv_set_map": (i, [vp, P(u16), P(u8), u32, d]),
         "prv_set_map_from_cloud": (i, [vp, P(f), P(u8), u64, d]),
@@ -242,6 +244,24 @@ def host_build_map(points, rgb, resolution):
     if rc:
         raise PrvError(rc, "prv_host_build_map")
     return keys[:n.value].copy(), out_rgb[:n.value].copy()
+
+
+def host_project_point_to_pixel(intr, point):
+    p = np.ascontiguousarray(point, dtype=np.float32)
+    out = np.zeros(2, dtype=np.float32)
+    rc = lib().prv_host_project_point_to_pixel(C.byref(intr), _p(p, C.c_float), _p(out, C.c_float))
+    if rc:
+        raise PrvError(rc, "prv_host_project_point_to_pixel")
+    return out
+
+
+def host_deproject_pixel_to_point(intr, pixel, depth=1.0):
+    p = np.ascontiguousarray(pixel, dtype=np.float32)
+    out = np.zeros(3, dtype=np.float32)
+    rc = lib().prv_host_deproject_pixel_to_point(C.byref(intr), _p(p, C.c_float), depth, _p(out, C.c_float))
+    if rc:
+        raise PrvError(rc, "prv_host_deproject_pixel_to_point")
+    return out
 
 
 def host_check_leaf_order(keys):

@@ -175,6 +175,82 @@ int prv_host_check_leaf_order(const uint16_t* keys, uint32_t N, uint32_t* first_
     return PRV_OK;
 }
 
+// rs2_project_point_to_pixel / rs2_deproject_pixel_to_point (Share_Data.hpp:92-137, :140-196) for every distortion model, float
+// arithmetic in the reference's evaluation order.  The reference is C++ with `using namespace std`, so tan / atan / abs on
+// float arguments are the float overloads: on models 3 (F-Theta) and 5 (Kannala-Brandt) the result is whatever THIS host's
+// libm returns, exactly like the reference compiled on this host.  The device never evaluates a transcendental: for those two
+// models prv_set_camera tabulates the deprojection of every integer pixel with this function and prv_cast_* (voxel mode)
+// projects the voxel centres with the other one on the host.
+int prv_host_project_point_to_pixel(const prv_intrinsics* in, const float point[3], float pixel_out[2]) {
+    if (!in || !point || !pixel_out) return PRV_ERR_INVALID;
+    float x = point[0] / point[2], y = point[1] / point[2];
+    if (in->model == 1 || in->model == 2) {
+        const float r2 = x * x + y * y;
+        const float f = 1 + in->coeffs[0] * r2 + in->coeffs[1] * r2 * r2 + in->coeffs[4] * r2 * r2 * r2;
+        x *= f;
+        y *= f;
+        const float dx = x + 2 * in->coeffs[2] * x * y + in->coeffs[3] * (r2 + 2 * x * x);
+        const float dy = y + 2 * in->coeffs[3] * x * y + in->coeffs[2] * (r2 + 2 * y * y);
+        x = dx;
+        y = dy;
+    } else if (in->model == 3 || in->model == 5) {
+        float r = std::sqrt(x * x + y * y);
+        if (r < 1.1920928955078125e-7f) r = 1.1920928955078125e-7f;  // FLT_EPSILON
+        float rd;
+        if (in->model == 3) {
+            rd = (float)(1.0f / in->coeffs[0] * std::atan(2 * r * std::tan(in->coeffs[0] / 2.0f)));
+        } else {
+            const float theta = std::atan(r);
+            const float theta2 = theta * theta;
+            const float series = 1 + theta2 * (in->coeffs[0] + theta2 * (in->coeffs[1] + theta2 * (in->coeffs[2] + theta2 * in->coeffs[3])));
+            rd = theta * series;
+        }
+        x *= rd / r;
+        y *= rd / r;
+    }
+    pixel_out[0] = x * in->fx + in->ppx;
+    pixel_out[1] = y * in->fy + in->ppy;
+    return PRV_OK;
+}
+
+int prv_host_deproject_pixel_to_point(const prv_intrinsics* in, const float pixel[2], float depth, float point_out[3]) {
+    if (!in || !pixel || !point_out) return PRV_ERR_INVALID;
+    if (in->model == 1) return PRV_ERR_UNSUPPORTED;  // the reference asserts (Share_Data.hpp:142)
+    float x = (pixel[0] - in->ppx) / in->fx;
+    float y = (pixel[1] - in->ppy) / in->fy;
+    if (in->model == 2) {
+        const float r2 = x * x + y * y;
+        const float f = 1 + in->coeffs[0] * r2 + in->coeffs[1] * r2 * r2 + in->coeffs[4] * r2 * r2 * r2;
+        const float ux = x * f + 2 * in->coeffs[2] * x * y + in->coeffs[3] * (r2 + 2 * x * x);
+        const float uy = y * f + 2 * in->coeffs[3] * x * y + in->coeffs[2] * (r2 + 2 * y * y);
+        x = ux;
+        y = uy;
+    } else if (in->model == 3 || in->model == 5) {
+        float rd = std::sqrt(x * x + y * y);
+        if (rd < 1.1920928955078125e-7f) rd = 1.1920928955078125e-7f;
+        float r;
+        if (in->model == 5) {
+            float theta = rd, theta2 = rd * rd;
+            for (int i = 0; i < 4; i++) {  // Newton on theta * series(theta^2) = rd
+                const float f = theta * (1 + theta2 * (in->coeffs[0] + theta2 * (in->coeffs[1] + theta2 * (in->coeffs[2] + theta2 * in->coeffs[3])))) - rd;
+                if (std::abs(f) < 1.1920928955078125e-7f) break;
+                const float df = 1 + theta2 * (3 * in->coeffs[0] + theta2 * (5 * in->coeffs[1] + theta2 * (7 * in->coeffs[2] + 9 * theta2 * in->coeffs[3])));
+                theta -= f / df;
+                theta2 = theta * theta;
+            }
+            r = std::tan(theta);
+        } else {
+            r = (float)(std::tan(in->coeffs[0] * rd) / std::atan(2 * std::tan(in->coeffs[0] / 2.0f)));
+        }
+        x *= r / rd;
+        y *= r / rd;
+    }
+    point_out[0] = depth * x;
+    point_out[1] = depth * y;
+    point_out[2] = depth;
+    return PRV_OK;
+}
+
 float prv_splat_focal(const prv_intrinsics* intr) {
     if (!intr) return 0.0f;
     // PCL 1.9.1 PCLVisualizer::setCameraParameters(intrinsics, extrinsics) (call: reference main.cpp:79):

@@ -140,7 +140,7 @@ def test_error_behaviour(prv, synth, ctx):
     c.set_map(w["keys"], None, 0.002)
     # unsupported / invalid cameras
     it = w["intr"]
-    for model, code in ((3, prv.ERR_UNSUPPORTED), (5, prv.ERR_UNSUPPORTED), (1, prv.ERR_UNSUPPORTED), (7, prv.ERR_INVALID)):
+    for model, code in ((1, prv.ERR_UNSUPPORTED), (7, prv.ERR_INVALID)):
         with pytest.raises(prv.PrvError) as e:
             c.set_camera(prv.make_intrinsics(it.width, it.height, it.fx, it.fy, it.ppx, it.ppy, model), 1.0)
         assert e.value.code == code
@@ -223,3 +223,41 @@ def test_gpu_ingest_matches_host_map_build(prv, orc, synth, name):
     b2, n2, _, _ = c.cast_views(w["pose_world"], w["init_pos"], mode=prv.MODE_DENSE)
     assert np.array_equal(b1, b2) and n1.sum() > 100
     c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model,coeffs", [(3, (0.9, 0, 0, 0, 0)), (5, (0.05, -0.01, 0.002, -0.0005, 0)), (4, (0.1, -0.2, 0.001, 0.002, 0))])
+def test_transcendental_distortion_models_match_the_oracle(prv, orc, synth, model, coeffs):
+    """rs2 models 3 (F-Theta) and 5 (Kannala-Brandt4), Share_Data.hpp:109-136, 156-190 (round 1 refused them): tan / atan are the
+    host libm's float overloads, so prv_set_camera tabulates the deprojection of every integer pixel on the host and the voxel-mode
+    projection runs on the host too -- the kernels never evaluate a transcendental and the results are the oracle's bit for bit
+    (dense cast, voxel-driven cast, precept cloud).  Model 4 (no distortion code in rs2) rides along."""
+    w = synth.build_workload(prv, "C1", n_views=4, size=(160, 120))
+    it0 = w["intr"]
+    it = prv.make_intrinsics(it0.width, it0.height, it0.fx, it0.fy, it0.ppx, it0.ppy, model, coeffs)
+    oit = orc.make_intrinsics(it.width, it.height, it.fx, it.fy, it.ppx, it.ppy, model, list(coeffs))
+    m = orc.Map.from_keys(w["keys"], w["map_rgb"], w["resolution"])
+    c = prv.Context(0)
+    try:
+        c.set_map(w["keys"], w["map_rgb"], w["resolution"])
+        c.set_camera(it, 1.0)
+        for variant in (prv.VARIANT_AXIS, prv.VARIANT_FAST):
+            c.set_variant(variant)
+            bits, counts, hit, depth = c.cast_views(w["pose_world"], w["init_pos"], mode=prv.MODE_DENSE, want_hit_rank=True, want_depth=True)
+            n_hit = 0
+            for v in range(w["n_views"]):
+                ok, r, d = m.cast_view_dense(oit, w["pose_world"][v], w["init_pos"][v])
+                assert np.array_equal(hit[v], r) and np.array_equal(depth[v], d), (model, variant, v)
+                n_hit += int((r != orc.NONE).sum())
+            assert n_hit > 1000
+        c.set_variant(prv.VARIANT_AXIS)
+        bv, cv, hv, _ = c.cast_views(w["pose_world"], w["init_pos"], mode=prv.MODE_VOXEL, want_hit_rank=True)
+        for v in range(w["n_views"]):
+            ok, o_pts, o_ranks = m.precept(oit, w["pose_world"][v], w["init_pos"][v])
+            assert np.array_equal(hv[v], o_ranks), (model, v)
+        pts, in_map = c.precept(w["pose_world"][1], w["init_pos"][1])
+        ok, o_pts, _ = m.precept(oit, w["pose_world"][1], w["init_pos"][1])
+        for f in ("x", "y", "z", "r", "g", "b"):
+            assert np.array_equal(pts[f], o_pts[f]), (model, f)
+    finally:
+        c.close()

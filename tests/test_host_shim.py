@@ -4,6 +4,7 @@ import os
 import subprocess
 
 import numpy as np
+import pytest
 
 
 def test_abi_exports_every_declared_symbol(prv):
@@ -147,3 +148,23 @@ def test_leaf_order_check(prv, synth):
     assert prv.host_check_leaf_order(big[order]) in (300, reference(big[order]))
     assert prv.host_check_leaf_order(big[order]) == reference(big[order])
     assert prv.host_check_leaf_order(big) == reference(big)
+
+
+@pytest.mark.parametrize("model", [0, 1, 2, 3, 4, 5])
+def test_host_camera_maths_equal_the_oracle_for_every_distortion_model(prv, orc, model):
+    """prv_host_project_point_to_pixel / prv_host_deproject_pixel_to_point (what the library tabulates for models 3 / 5) against
+    the oracle's rs2_* restatement, which tests/test_oracle_kat.py pins bit for bit to the reference's own compiled code."""
+    rng = np.random.default_rng(300 + model)
+    for coeffs in ((0.12042199820280075, -0.21373499929904938, -0.0021210000850260258, 0.0053860000334680080, 0.0), (0.31, -0.47, 0.013, -0.009, 0.12),
+                   (0.9, 0, 0, 0, 0)):
+        it = prv.make_intrinsics(1280, 720, 915.60669, 913.32666, 647.14532, 372.51532, model, coeffs)
+        oit = orc.make_intrinsics(1280, 720, 915.60669, 913.32666, 647.14532, 372.51532, model, coeffs)
+        for _ in range(300):
+            pt = np.array([rng.normal() * 0.2, rng.normal() * 0.2, 0.05 + rng.random()], dtype=np.float32)
+            assert prv.host_project_point_to_pixel(it, pt).tobytes() == orc.project_point_to_pixel(oit, pt).tobytes()
+            px = np.floor(np.array([rng.random() * 1281, rng.random() * 721], dtype=np.float32))
+            if model == 1:
+                with pytest.raises(prv.PrvError):
+                    prv.host_deproject_pixel_to_point(it, px)
+            else:
+                assert prv.host_deproject_pixel_to_point(it, px, 1.0).tobytes() == orc.deproject_pixel_to_point(oit, px, 1.0).tobytes()
