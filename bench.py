@@ -159,7 +159,7 @@ def _config(name, w, args, world, strong, l2_note):
     return {"workload": _workload_text(name, w), "objects_per_step": 1 if (strong or world == 1) else world, "views": w["n_views"], "width": w["W"],
             "height": w["H"], "voxels": int(len(w["keys"])), "resolution_m": w["resolution"], "l2": l2_note,
             "sharding": ("views interleaved over %d ranks + all-gather of the coverage rows in the timed step (%s)" %
-                         (world, "peer-memory stores over NVLink fused into the count kernel" if args.gather == "p2p" else "ncclAllGather")) if strong else
+                         (world, "peer-memory stores over NVLink fused into the count kernel" if getattr(args, "gather_used", args.gather) == "p2p" else "ncclAllGather")) if strong else
                         ("one object per rank, no collective" if world > 1 else "single GPU"),
             "variant": args.variant, "brick": args.brick, "brick_entry": bool(args.brick_entry), "stage_smem": bool(args.stage_smem), "stage_l2": bool(args.stage_l2)}
 
@@ -228,10 +228,23 @@ class Runner:
             ctx.comm_init(bytes(t.cpu().tolist()), rank, world)
             self.p2p = args.gather == "p2p"
             if self.p2p:
-                # peer-memory exchange: every rank's arena handle to every rank, then rows travel as NVLink stores from the count kernel
-                handles = [None] * world
-                dist.all_gather_object(handles, ctx.p2p_export())
-                ctx.p2p_import(handles, rank, world)
+                # peer-memory exchange: every rank's arena handle to every rank, then rows travel as NVLink stores from the count kernel.
+                # If any rank cannot map a peer (no P2P / IPC between the devices) every rank uses ncclAllGather instead; the
+                # transport actually used is named in config.sharding.
+                ok = 1
+                try:
+                    handles = [None] * world
+                    dist.all_gather_object(handles, ctx.p2p_export())
+                    ctx.p2p_import(handles, rank, world)
+                except prv.PrvError as exc:
+                    sys.stderr.write("bench.py: rank %d: peer-memory exchange unavailable (%s); falling back to ncclAllGather\n" % (rank, exc))
+                    ok = 0
+                flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                if int(flag.item()) == 0:
+                    ctx.comm_destroy_p2p()
+                    self.p2p = False
+            args.gather_used = "p2p" if self.p2p else "nccl"
             ctx.set_views(self.pose, self.init, view_ids=ids)
             dist.barrier()
             self.local_views = int(real.sum())

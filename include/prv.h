@@ -271,6 +271,7 @@ int prv_allgather_bitsets_async(prv_ctx* ctx);
  * nranks * V * (words * 8 + 4), the gathered table + ids of one step (0 = 16 MB; the 1024-view workload needs 1.8 MB). */
 int prv_comm_p2p_export(prv_ctx* ctx, void* handle_out_64, uint64_t table_bytes_max);
 int prv_comm_p2p_import(prv_ctx* ctx, const void* handles, int rank, int nranks);
+int prv_comm_p2p_close(prv_ctx* ctx); /* unmap the peer arenas; prv_allgather_bitsets_async goes back to NCCL (prv_comm_destroy calls it too) */
 /* the table the replicated selection runs over after the all-gather: nranks * V rows in rank order and their view ids
  * (rows_out [nrows][words], ids_out [nrows]; either may be NULL; *nrows_out = nranks * V).  Synchronises. */
 int prv_get_gathered(prv_ctx* ctx, uint64_t* rows_out, uint32_t* ids_out, uint32_t* nrows_out);

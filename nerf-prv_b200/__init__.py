@@ -141,6 +141,7 @@ def lib():
         "prv_get_gathered": (i, [vp, P(u64), P(u32), P(u32)]),
         "prv_comm_p2p_export": (i, [vp, vp, u64]),
         "prv_comm_p2p_import": (i, [vp, vp, i, i]),
+        "prv_comm_p2p_close": (i, [vp]),
         "prv_comm_destroy": (i, [vp]),
     }
     for name, (res, args) in sig.items():
@@ -556,6 +557,10 @@ class Context:
         buf = b"".join(handles)
         assert len(buf) == 64 * nranks
         self._chk(lib().prv_comm_p2p_import(self._h, buf, rank, nranks))
+
+    def comm_destroy_p2p(self):
+        """Unmap the peer arenas (the NCCL communicator, if any, is kept)."""
+        self._chk(lib().prv_comm_p2p_close(self._h))
 
     def get_gathered(self):
         """(rows [nranks*V][words], view ids [nranks*V]) of the all-gathered coverage table."""

@@ -41,9 +41,14 @@ __global__ void __launch_bounds__(256) splat_resolve_kernel(const unsigned long 
     unsigned long long* s_hmin = s_tile + tw * th;
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
     const unsigned long long* src = corner + (size_t)view_local * Hc * Wc;
-    for (int t = threadIdx.x; t < tw * th; t += blockDim.x) {
-        const int cx = x0 + t % tw, cy = y0 + t / tw;
-        s_tile[t] = (cx < Wc && cy < Hc) ? src[(size_t)cy * Wc + cx] : ~0ull;
+    // tile rows by warp, columns by lane (no division by the tile width): 32 coalesced columns, then the s - 1 extra ones
+    for (int r = threadIdx.x >> 5; r < th; r += 8) {
+        const int cy = y0 + r;
+        const unsigned long long* row = src + (size_t)cy * Wc;
+        for (int c = threadIdx.x & 31; c < tw; c += 32) {
+            const int cx = x0 + c;
+            s_tile[r * tw + c] = (cx < Wc && cy < Hc) ? row[cx] : ~0ull;
+        }
     }
     __syncthreads();
     for (int t = threadIdx.x; t < 32 * th; t += blockDim.x) {

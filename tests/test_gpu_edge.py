@@ -206,9 +206,11 @@ def test_gpu_ingest_matches_host_map_build(prv, orc, synth, name):
     w = synth.build_workload(prv, name, n_views=2, size=(64, 48))
     cloud = w["cloud"].copy()
     rgb = w["cloud_rgb"].copy()
-    # a few points outside the key range (coordToKeyChecked fails -> skipped) and duplicates with different colours
-    cloud = np.concatenate([cloud, [[70.0, 0, 0], [0, -70.0, 0]], cloud[:50]]).astype(np.float32)
-    rgb = np.concatenate([rgb, [[1, 2, 3], [4, 5, 6]], 255 - rgb[:50]]).astype(np.uint8)
+    # a few points outside the key range (coordToKeyChecked fails -> skipped), non-finite points (the clouds are is_dense = false:
+    # (int)floor(NaN) is INT_MIN on the reference's x86 -> rejected; 0 in CUDA, hence the range test on the double) and duplicates
+    # with different colours
+    cloud = np.concatenate([cloud, [[70.0, 0, 0], [0, -70.0, 0], [np.nan, 0, 0], [0.01, np.inf, 0], [0, 0, -np.inf], [3.0e9, 0, 0]], cloud[:50]]).astype(np.float32)
+    rgb = np.concatenate([rgb, [[1, 2, 3], [4, 5, 6], [7, 8, 9], [9, 8, 7], [6, 5, 4], [3, 2, 1]], 255 - rgb[:50]]).astype(np.uint8)
     c = prv.Context(0)
     c.set_map_from_cloud(cloud, rgb, w["resolution"])
     keys, col = c.get_map()
