@@ -41,13 +41,19 @@ __global__ void __launch_bounds__(256) splat_resolve_kernel(const unsigned long 
     unsigned long long* s_hmin = s_tile + tw * th;
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 8;
     const unsigned long long* src = corner + (size_t)view_local * Hc * Wc;
-    // tile rows by warp, columns by lane (no division by the tile width): 32 coalesced columns, then the s - 1 extra ones
-    for (int r = threadIdx.x >> 5; r < th; r += 8) {
-        const int cy = y0 + r;
-        const unsigned long long* row = src + (size_t)cy * Wc;
-        for (int c = threadIdx.x & 31; c < tw; c += 32) {
-            const int cx = x0 + c;
-            s_tile[r * tw + c] = (cx < Wc && cy < Hc) ? row[cx] : ~0ull;
+    // flat tile index t -> (row, column) carried incrementally: one division per thread instead of one per element
+    {
+        const int dr = (int)blockDim.x / tw, dc = (int)blockDim.x % tw;
+        int r = (int)threadIdx.x / tw, c = (int)threadIdx.x % tw;
+        for (int t = threadIdx.x; t < tw * th; t += blockDim.x) {
+            const int cx = x0 + c, cy = y0 + r;
+            s_tile[t] = (cx < Wc && cy < Hc) ? src[(size_t)cy * Wc + cx] : ~0ull;
+            c += dc;
+            r += dr;
+            if (c >= tw) {
+                c -= tw;
+                r++;
+            }
         }
     }
     __syncthreads();
