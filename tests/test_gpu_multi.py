@@ -45,3 +45,17 @@ def test_view_sharded_c3_matches_the_oracle_on_every_rank(n, gather):
     assert len(d["per_rank"]) == n and all(r_["allgather_ms"] > 0 for r_ in d["per_rank"])
     assert ("peer-memory" in d["config"]["sharding"]) == (gather == "p2p")
     assert sum(r_["local_views"] for r_ in d["per_rank"]) == 1024
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [2, 4])
+def test_small_sharded_paths(n):
+    """Every transport of the coverage rows (peer-memory stores fused into the count kernel, peer-memory stores from the scoring
+    stream, ncclAllGather), uneven view split with padding rows, five pipelined steps at a time: gathered table, counts and greedy
+    against the oracle on every rank (tests/multi_worker.py)."""
+    if _gpus() < n:
+        pytest.skip("needs %d GPUs" % n)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1", "--master-port",
+           str(29750 + n), os.path.join(ROOT, "tests", "multi_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and ("MULTI_WORKER_OK world=%d" % n) in r.stdout, (r.stdout[-2000:], r.stderr[-3000:])
