@@ -629,7 +629,7 @@ def main():
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
     ap.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--variant", type=int, default=2)
-    ap.add_argument("--brick", type=int, default=8, choices=[4, 8, 16], help="prv_set_brick_cull: brick edge of the conservative cull in voxels")
+    ap.add_argument("--brick", type=int, default=0, choices=[0, 4, 8, 16], help="prv_set_brick_cull: brick edge of the conservative cull in voxels")
     ap.add_argument("--brick-entry", type=int, default=1, choices=[0, 1], help="prv_set_brick_cull: start the exact march at the first set brick")
     ap.add_argument("--stage-smem", type=int, default=1, choices=[0, 1], help="A/B: padded bitmap staged in the march blocks' shared memory")
     ap.add_argument("--stage-l2", type=int, default=0, choices=[0, 1], help="A/B: L2 persisting window over the padded bitmap")

@@ -114,7 +114,8 @@ int         prv_device_info(prv_ctx* ctx, int* sm_count, int* cc_major, int* cc_
 int         prv_sync(prv_ctx* ctx);
 int         prv_set_variant(prv_ctx* ctx, int variant);
 /* Tuning of the conservative brick cull in front of the exact march (variant AXIS).  `cell` = edge of the bricks of the
- * coarse occupancy grid in voxels (4, 8 or 16; default 8).  With enter_at_brick != 0 (default) the exact march of a
+ * coarse occupancy grid in voxels (4, 8 or 16; 0 = chosen by map size, the default: 4 while the AABB spans at most 64 voxels,
+ * else 8).  With enter_at_brick != 0 (default) the exact march of a
  * surviving ray starts where the ray enters the first set brick of the cull's walk (grown by one voxel) instead of at the
  * AABB face: the voxels in between are provably empty and are crossed by the cheap per-axis additions.  Results are
  * identical for every setting; only the probes_in / marched counters of prv_cast_stats move.

@@ -325,8 +325,8 @@ class Context:
     def set_variant(self, v):
         self._chk(lib().prv_set_variant(self._h, v))
 
-    def set_brick_cull(self, cell=8, enter_at_brick=True):
-        """Brick edge of the conservative cull (4, 8 or 16 voxels) and whether the exact march starts at the first set
+    def set_brick_cull(self, cell=0, enter_at_brick=True):
+        """Brick edge of the conservative cull (4, 8 or 16 voxels; 0 = by map size) and whether the exact march starts at the first set
         brick.  Applies to the next set_map; results are identical for every setting."""
         self._chk(lib().prv_set_brick_cull(self._h, cell, 1 if enter_at_brick else 0))
 

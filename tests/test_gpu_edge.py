@@ -263,3 +263,61 @@ def test_transcendental_distortion_models_match_the_oracle(prv, orc, synth, mode
             assert np.array_equal(pts[f], o_pts[f]), (model, f)
     finally:
         c.close()
+
+
+@pytest.mark.gpu
+def test_abi_guards_of_round_2(prv, synth):
+    """result capacity of prv_get_greedy, validated view ids, V mismatch, cast statistics of the LATEST cast."""
+    import ctypes as C
+    w = synth.build_workload(prv, "C1", n_views=6, size=(96, 72))
+    c = prv.Context(0)
+    try:
+        L = prv.lib()
+        c.set_map(w["keys"], w["map_rgb"], w["resolution"])
+        c.set_camera(w["intr"], 1.0)
+        c.set_views(w["pose_world"], w["init_pos"])
+        c.cast_async(prv.MODE_DENSE, False)
+        c.greedy_async(0, 64)
+        # a buffer sized for a smaller max_iter than the async call ran with: nothing is written, the needed size is reported
+        seq = np.full(2, 0xABABABAB, dtype=np.uint32)
+        gains = np.full(2, 0xABABABAB, dtype=np.uint32)
+        n = C.c_uint32(0)
+        rc = L.prv_get_greedy(c._h, seq.ctypes.data_as(C.POINTER(C.c_uint32)), gains.ctypes.data_as(C.POINTER(C.c_uint32)), 2, C.byref(n), None)
+        full_seq, full_gain, _ = c.get_greedy()
+        assert len(full_seq) > 2
+        assert rc == prv.ERR_INVALID and n.value == len(full_seq) and np.all(seq == 0xABABABAB) and np.all(gains == 0xABABABAB)
+        assert b"hold 2" in L.prv_last_error(c._h)
+        # get_greedy(10) after greedy_async(0, 64) (the advisor's heap-corruption case) sizes from the remembered max_iter
+        s10, g10, _ = c.get_greedy(10)
+        assert s10.tolist() == full_seq.tolist()
+        # view ids: duplicates, sentinels, V mismatch
+        V = w["n_views"]
+        for bad in ([0, 1, 2, 2, 4, 5], [0, 1, 2, 3, 4, 0xFFFFFFF0], [0, 1, 2, 3, 4, 0xFFFFFFFF]):
+            with pytest.raises(prv.PrvError) as e:
+                c.set_views(w["pose_world"], w["init_pos"], view_ids=np.array(bad, dtype=np.uint32))
+            assert e.value.code == prv.ERR_INVALID
+        ids = np.arange(V, dtype=np.uint32) * 3 + 1  # (monotone: ties would break the same way)
+        assert L.prv_set_view_ids(c._h, ids.ctypes.data_as(C.POINTER(C.c_uint32)), V) == 0
+        pw = np.ascontiguousarray(w["pose_world"][:4].reshape(-1, 16))
+        ip = np.ascontiguousarray(w["init_pos"][:4])
+        rc = L.prv_set_views(c._h, pw.ctypes.data_as(C.POINTER(C.c_double)), ip.ctypes.data_as(C.POINTER(C.c_double)), 4)
+        assert rc == prv.ERR_INVALID and b"prv_set_view_ids gave 6 ids" in L.prv_last_error(c._h)
+        c.set_views(w["pose_world"], w["init_pos"], view_ids=ids)  # same V: accepted, ties break on these ids
+        c.cast_async(prv.MODE_DENSE, False)
+        seq_ids, _ = c.greedy(int(ids[0]), 64)
+        assert seq_ids[0] == ids[0] and set(seq_ids.tolist()) <= set(ids.tolist())
+        assert [int(np.where(ids == s)[0][0]) for s in seq_ids] == full_seq.tolist()  # the same views under other names
+        # statistics belong to the latest cast, whatever variant is selected afterwards
+        c.set_views(w["pose_world"], w["init_pos"])
+        c.set_variant(prv.VARIANT_FAST)
+        c.cast_async(prv.MODE_DENSE, False)
+        c.set_variant(prv.VARIANT_AXIS)
+        st = c.get_cast_stats()
+        assert st["rays"] == V * 96 * 72 and st["marched"] == st["rays"]
+        c.cast_async(prv.MODE_DENSE, False)
+        st2 = c.get_cast_stats()
+        assert st2["rays"] == st["rays"] and st2["hits"] == st["hits"] and st2["marched"] < st["marched"]
+        t = c.get_timing()
+        assert t["dropped"] == 0
+    finally:
+        c.close()
