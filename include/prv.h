@@ -102,6 +102,7 @@ typedef struct prv_timing {
     float    resolve_ms;  uint32_t resolve_launches;
     float    other_ms;    uint32_t other_launches;
     float    gather_ms;   uint32_t gather_launches;  /* NCCL all-gather of the coverage rows (scoring stream) */
+    float    flush_ms;    /* prv_flush_l2 memsets (not work of the path: benchmarks subtract it) */
     uint32_t dropped;     /* spans not recorded because 65536 were already held: call prv_timing_reset more often */
 } prv_timing;
 
@@ -255,7 +256,8 @@ int prv_reset_counters(prv_ctx* ctx);
 int prv_get_counters(prv_ctx* ctx, uint64_t* kernel_launches, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 /* size of the dense occupancy bitmap in HBM (B_occ of the roofline formula) */
 int prv_map_bytes(prv_ctx* ctx, uint64_t* bitmap_bytes);
-/* writes >L2-size scratch so the next kernel starts cold */
+/* writes >L2-size scratch (256 MiB) on the cast stream so the next kernels start cold; its device time is reported separately
+ * (prv_timing::flush_ms) */
 int prv_flush_l2(prv_ctx* ctx);
 
 /* ---------------------------------------------------------------- multi-GPU (one process per GPU; NCCL over NVLink) */

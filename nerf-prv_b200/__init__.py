@@ -48,7 +48,7 @@ class Timing(C.Structure):
                 ("count_ms", C.c_float), ("count_launches", C.c_uint32), ("greedy_ms", C.c_float), ("greedy_launches", C.c_uint32),
                 ("splat_ms", C.c_float), ("splat_launches", C.c_uint32), ("resolve_ms", C.c_float), ("resolve_launches", C.c_uint32),
                 ("other_ms", C.c_float), ("other_launches", C.c_uint32), ("gather_ms", C.c_float), ("gather_launches", C.c_uint32),
-                ("dropped", C.c_uint32)]
+                ("flush_ms", C.c_float), ("dropped", C.c_uint32)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

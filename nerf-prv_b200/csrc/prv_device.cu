@@ -43,7 +43,7 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-enum KClass { K_CAST = 0, K_CULL, K_MARCH, K_PROJECT, K_COUNT, K_GREEDY, K_SPLAT, K_RESOLVE, K_OTHER, K_GATHER, K_NCLASS };
+enum KClass { K_CAST = 0, K_CULL, K_MARCH, K_PROJECT, K_COUNT, K_GREEDY, K_SPLAT, K_RESOLVE, K_OTHER, K_GATHER, K_FLUSH, K_NCLASS };
 
 struct TimedSpan {
     int cls;
@@ -77,7 +77,7 @@ struct prv_ctx {
     // double-buffered (d_rows[2]); events order producer and consumer (rows_ready / rows_free).
     cudaStream_t stream = nullptr;
     cudaStream_t score_stream = nullptr;
-    cudaEvent_t ev_rows_ready[2] = {nullptr, nullptr}, ev_rows_free[2] = {nullptr, nullptr}, ev_join = nullptr;
+    cudaEvent_t ev_rows_ready[2] = {nullptr, nullptr}, ev_rows_free[2] = {nullptr, nullptr}, ev_join = nullptr, ev_flush = nullptr;
     bool rows_free_pending[2] = {false, false};
     int cur = 0;  // row buffer of the latest cast
     char err[512] = {0};
@@ -826,6 +826,7 @@ int prv_create(prv_ctx** out, int device) {
     for (auto& s : ctx->slots) cudaEventCreate(&s);
     cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_flush, cudaEventDisableTiming);
     for (int i = 0; i < 2; i++) {
         cudaEventCreateWithFlags(&ctx->ev_rows_ready[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_rows_free[i], cudaEventDisableTiming);
@@ -855,6 +856,7 @@ void prv_destroy(prv_ctx* ctx) {
     for (auto& s : ctx->slots) cudaEventDestroy(s);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_flush) cudaEventDestroy(ctx->ev_flush);
     for (int i = 0; i < 2; i++) {
         if (ctx->ev_rows_ready[i]) cudaEventDestroy(ctx->ev_rows_ready[i]);
         if (ctx->ev_rows_free[i]) cudaEventDestroy(ctx->ev_rows_free[i]);
@@ -1567,6 +1569,7 @@ int prv_get_timing(prv_ctx* ctx, prv_timing* out) {
     out->resolve_ms = ms[K_RESOLVE]; out->resolve_launches = cnt[K_RESOLVE];
     out->other_ms = ms[K_OTHER];     out->other_launches = cnt[K_OTHER];
     out->gather_ms = ms[K_GATHER];   out->gather_launches = cnt[K_GATHER];
+    out->flush_ms = ms[K_FLUSH];
     out->dropped = ctx->spans_dropped;
     return PRV_OK;
 }
@@ -1613,7 +1616,13 @@ int prv_flush_l2(prv_ctx* ctx) {
     const size_t bytes = (size_t)256 << 20;  // > 126 MB L2
     int rc;
     if ((rc = ensure(ctx, ctx->d_flush, bytes))) return rc;
-    CU(cudaMemsetAsync(ctx->d_flush.p, 0x5A, bytes, ctx->stream));
+    {
+        Span s(ctx, K_FLUSH, 0);  // timed on its own (prv_timing::flush_ms) so a caller can take it out of a bracket around several steps
+        CU(cudaMemsetAsync(ctx->d_flush.p, 0x5A, bytes, ctx->stream));
+    }
+    // whatever is enqueued on the scoring stream from here on starts after the flush too: nothing of the path runs underneath it
+    CU(cudaEventRecord(ctx->ev_flush, ctx->stream));
+    CU(cudaStreamWaitEvent(ctx->score_stream, ctx->ev_flush, 0));
     return PRV_OK;
 }
 
