@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B of the staging options (prv_set_staging) and of march-kernel shapes (PRV_MARCH_CFG) on C2 / C3, then ncu on C3
+# A/B of the staging options (prv_set_staging) on C2 / C3, then ncu on C3.  (The march-kernel shape variants of profiles/r2_staging_ab.md
+# -- 2 probes in flight, 128-thread blocks, coarse kernel at 6 blocks/SM -- were compile-time switches that have been removed.)
 O=gpurun_out/ab
 mkdir -p $O
 run() { # tag workload extra-args...
@@ -12,9 +13,6 @@ for WL in C2 C3; do
   run base $WL
   run smem $WL --stage-smem 1
   run l2 $WL --stage-l2 1
-  PRV_MARCH_CFG=1 run u2 $WL
-  PRV_MARCH_CFG=2 run b128u4 $WL
-  PRV_MARCH_CFG=3 run b128u2 $WL
-  PRV_COARSE_MINB=6 run coarse6 $WL
+  run nosmem $WL --stage-smem 0
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"march_kernel|coarse_kernel|cull_kernel" -s 9 -c 3 -o $O/prof_c3 python bench.py --workload C3 --steps 1 --warmup 3 --no-cpu-baseline --no-extras --no-sustained --no-parity > $O/prof_c3.log 2>&1
