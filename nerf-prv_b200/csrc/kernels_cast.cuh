@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
                 keep = true;  // this view needs the literal march (max-range test): no cull
             } else {
                 float dx, dy, dz;
-                ray_direction_approx(p.cam, vc, (float)px, (float)py, dx, dy, dz);
+                ray_direction_approx_px(p.cam, vc, px, py, dx, dy, dz);
                 keep = !coarse_miss(p.map, vc, dx, dy, dz, cell);
             }
             if (!keep && p.pix_hit) {

@@ -1030,6 +1030,7 @@ static int set_map_impl(prv_ctx* ctx, const uint16_t* keys, const uint8_t* rgb, 
     }
     ctx->map.coarse = ptr<uint32_t>(ctx->d_coarse);
     for (int a = 0; a < 3; a++) ctx->map.nc[a] = nc[a];
+    for (int a = 0; a < 3; a++) ctx->map.nhi[a] = (float)n[a] + 1.0f;
     ctx->map.cs = cs;
     ctx->map.inv_cs = 1.0f / (float)cs;
     {   // row / (n1 + 2) of the march epilogue as a multiply-high: exact while row * (n1 + 2) < 2^32

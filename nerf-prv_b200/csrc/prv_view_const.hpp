@@ -55,6 +55,8 @@ inline void make_view_const(const ViewSetup& ctx, const double* pose_world, cons
         vc.origin[a] = ok ? (float)prv::key_to_coord(k[a], ctx.resolution) : 0.0f;
     }
     for (int a = 0; a < 3; a++) vc.tnum[a][0] = vc.tnum[a][1] = 0.0;
+    for (int a = 0; a < 3; a++) vc.ovox[a] = 0.0f;
+    vc.pad_ = 0.0f;
     if (!ok) return;
     for (int r = 0; r < 3; r++) vc.posef[4 * r + 3] = (float)(pw(r, 3) - (double)vc.origin[r]);
     vc.flags |= kViewInMap;
@@ -63,6 +65,7 @@ inline void make_view_const(const ViewSetup& ctx, const double* pose_world, cons
         uint16_t kk;
         if (prv::coord_to_key_checked((double)vc.origin[a], rf, kk)) vc.okey[a] = kk;
     }
+    for (int a = 0; a < 3; a++) vc.ovox[a] = (float)(vc.okey[a] - ctx.lo[a]) + 0.5f;
     // castRay's voxelBorder - origin per axis and step sign (OccupancyOcTreeBase::castRay: voxelBorder = keyToCoord(key) +
     // step * resolution * 0.5; tMax = (voxelBorder - (double)origin) / direction), operation by operation
     for (int a = 0; a < 3; a++)

@@ -97,6 +97,7 @@ bool build_map(HostMap& hm, const uint16_t* keys, const uint8_t* rgb, uint32_t N
         m.lo[a] = lo[a];
         m.n[a] = hi[a] - lo[a] + 1;
         m.nc[a] = (m.n[a] + brick_cs - 1) / brick_cs;
+        m.nhi[a] = (float)m.n[a] + 1.0f;
         // AABB grown by 2 voxels, metres
         m.bmin[a] = (float)((double)(lo[a] - 2 - prv::kTreeMaxVal) * resolution);
         m.bmax[a] = (float)((double)(lo[a] + m.n[a] + 2 - prv::kTreeMaxVal) * resolution);
