@@ -65,54 +65,9 @@ __device__ __forceinline__ void write_hit(const CastParams& p, const ViewConst& 
 // kernel 1 (cull_kernel):   every 32x32-pixel region against the AABB; dismissed regions are filled with "no hit", the rest -> region queue
 // kernel 2 (coarse_kernel): every pixel of the queued regions, conservative slab test + coarse-brick walk; survivors -> queue 2
 // kernel 3 (march_kernel):  dense warps over queue 2, the exact castRay march
-// Kernels 2 and 3 are persistent: kernel 2's blocks pull 256-ray chunks, kernel 3's warps 32-ray chunks of a flattened
+// Kernels 2 and 3 are persistent: kernel 2's blocks pull 256-pixel row-tiles, kernel 3's warps 32-ray chunks of a flattened
 // (view, chunk) list with an atomic ticket, so expensive and cheap chunks balance across the 148 SMs and there is no
-// partial last wave.
-
-// block-level stream compaction of `keep` lanes into a per-view queue: one atomic per block
-__device__ __forceinline__ void block_append(bool keep, uint32_t value, uint32_t* queue_view, uint32_t* count_view, uint32_t* s_woff, uint32_t* s_base) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
-    if (lane == 0) s_woff[warp] = __popc(bal);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int w = 0; w < 8; w++) {
-            const uint32_t c = s_woff[w];
-            s_woff[w] = tot;
-            tot += c;
-        }
-        *s_base = tot ? atomicAdd(count_view, tot) : 0u;
-    }
-    __syncthreads();
-    if (keep) queue_view[*s_base + s_woff[warp] + __popc(bal & ((1u << lane) - 1u))] = value;
-    __syncthreads();  // s_woff / s_base are reused by the next chunk
-}
-
-// same, two parallel queues (pixel, entry brick)
-__device__ __forceinline__ void block_append2(bool keep, uint32_t v1, uint32_t v2, uint32_t* q1, uint32_t* q2, uint32_t* count_view, uint32_t* s_woff,
-                                              uint32_t* s_base) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
-    if (lane == 0) s_woff[warp] = __popc(bal);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t tot = 0;
-        for (int w = 0; w < 8; w++) {
-            const uint32_t c = s_woff[w];
-            s_woff[w] = tot;
-            tot += c;
-        }
-        *s_base = tot ? atomicAdd(count_view, tot) : 0u;
-    }
-    __syncthreads();
-    if (keep) {
-        const uint32_t pos = *s_base + s_woff[warp] + __popc(bal & ((1u << lane) - 1u));
-        q1[pos] = v1;
-        q2[pos] = v2;
-    }
-    __syncthreads();
-}
+// partial last wave.  Both compact their survivors per warp (one atomic per warp).
 
 // One block per kCullRegions consecutive 32x32-pixel regions of one row of one view (blockIdx = (region group, region
 // row, view)): the view constants are fetched once and the region tests of the group run side by side (one warp each),
@@ -228,33 +183,28 @@ template <int MINB, bool MASKED>
 __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
     __shared__ ViewConst s_vc;
     __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
-    __shared__ uint32_t s_woff[8];
-    __shared__ uint32_t s_base;
-    __shared__ uint32_t s_ticket, s_vl;
-    if (threadIdx.x == 0) s_vl = 0;
-    __shared__ uint32_t s_rays[8];
+    __shared__ uint32_t s_ticket[2], s_vl[2];  // double-buffered: ONE block barrier per tile (the survivors are appended per warp)
+    if (threadIdx.x == 0) s_vl[1] = 0;
     build_chunk_prefix(p.qcount + p.view_base, p.nviews, s_prefix, 256u, 4u);
     const uint32_t total = s_prefix[p.nviews];
     uint32_t cur_view = 0xFFFFFFFFu;
-    uint32_t vl = 0;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (;;) {
+    for (uint32_t it = 0;; it++) {
+        const uint32_t slot = it & 1u;
         if (threadIdx.x == 0) {
             const uint32_t t = atomicAdd(p.tickets + 0, 1u);
-            s_ticket = t;
-            if (t < total) {
-                uint32_t v = s_vl;
+            s_ticket[slot] = t;
+            uint32_t v = s_vl[slot ^ 1u];
+            if (t < total)
                 while (s_prefix[v + 1] <= t) v++;  // tickets grow monotonically within a block: amortised O(1)
-                s_vl = v;
-            }
+            s_vl[slot] = v;
         }
-        __syncthreads();
-        const uint32_t g = s_ticket;
+        __syncthreads();  // (every warp has finished the previous tile: s_vc and the other ticket slot may be rewritten)
+        const uint32_t g = s_ticket[slot];
         if (g >= total) break;
-        vl = s_vl;
+        const uint32_t vl = s_vl[slot];
         const uint32_t view = vl + p.view_base;
         if (view != cur_view) {
-            __syncthreads();
             load_view_prefix(s_vc, p.views + view);
             cur_view = view;
         }
@@ -262,8 +212,9 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
         // chunk = one 32x8 row-tile of a queued region; a warp covers an 8x4 patch of it
         const uint32_t c = g - s_prefix[vl];
         const uint32_t region = p.queue[(size_t)view * p.rqueue_cap + (c >> 2)];
-        const int px = (int)((region & 0xFFFFu) << 5) + ((warp & 3) << 3) + (lane & 7);
-        const int py = (int)((region >> 16) << 5) + (int)((c & 3u) << 3) + ((warp >> 2) << 2) + (lane >> 3);
+        const int x0 = (int)((region & 0xFFFFu) << 5), y0 = (int)((region >> 16) << 5) + (int)((c & 3u) << 3);
+        const int px = x0 + ((warp & 3) << 3) + (lane & 7);
+        const int py = y0 + ((warp >> 2) << 2) + (lane >> 3);
         const uint32_t pid = ((uint32_t)py << 16) | (uint32_t)px;  // queues carry (y,x) packed: no division downstream
         bool active = px < p.GW && py < p.GH;
         if (MASKED && active) {
@@ -287,16 +238,23 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
                 if (p.pix_depth) p.pix_depth[o] = 0.0f;
             }
         }
-        const uint32_t nact = __popc(__ballot_sync(0xFFFFFFFFu, active));
-        if (lane == 0) s_rays[warp] = nact;
-        if (p.queue2b)
-            block_append2(keep, pid, cell, p.queue2 + (size_t)view * p.queue_cap, p.queue2b + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
-        else
-            block_append(keep, pid, p.queue2 + (size_t)view * p.queue_cap, p.qcount2 + view, s_woff, &s_base);
-        if (threadIdx.x == 0) {  // (block_append's barriers order the s_rays stores before, and its last one the reuse after)
-            uint32_t rays = 0;
-            for (int w = 0; w < 8; w++) rays += s_rays[w];
-            if (rays) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)rays);
+        // rays of the tile: dense mode by geometry (one atomic per tile), voxel mode by counting the masked pixels per warp
+        if (MASKED) {
+            const uint32_t nact = __popc(__ballot_sync(0xFFFFFFFFu, active));
+            if (lane == 0 && nact) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)nact);
+        } else if (threadIdx.x == 0) {
+            const int w = min(32, p.GW - x0), h = min(8, p.GH - y0);
+            if (w > 0 && h > 0) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)(w * h));
+        }
+        // survivors -> queue 2 (+ entry brick), compacted per warp: one atomic per warp, no block barrier
+        const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+        uint32_t base = 0;
+        if (lane == 0 && bal) base = atomicAdd(p.qcount2 + view, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (keep) {
+            const size_t pos = (size_t)view * p.queue_cap + base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+            p.queue2[pos] = pid;
+            if (p.queue2b) p.queue2b[pos] = cell;
         }
     }
 }

@@ -593,8 +593,8 @@ def test_kernels_are_race_free_under_threadsanitizer(tmp_path):
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tsan", "run_kernels_under_tsan.py"), str(lib)], env=env, capture_output=True, text=True,
                        timeout=600)
-    if "KERNELS-RAN-UNDER-TSAN" not in r.stdout and "ThreadSanitizer" not in r.stderr:
-        pytest.skip("the interpreter does not run under libtsan here: " + r.stderr[-300:])
+    if "KERNELS-RAN-UNDER-TSAN" not in r.stdout and "ThreadSanitizer" not in r.stderr and "Traceback" not in r.stderr:
+        pytest.skip("the interpreter does not run under libtsan here: " + r.stderr[-300:])  # (a Python error in the child is a failure, not a skip)
     assert "KERNELS-RAN-UNDER-TSAN" in r.stdout, r.stderr[-2000:]
     assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[:4000]
 

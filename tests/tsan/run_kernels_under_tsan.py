@@ -19,14 +19,14 @@ import test_kernel_on_host as T  # noqa: E402
 poh = C.CDLL(sys.argv[1])
 w = synth.build_workload(prv, "C1", n_views=3, size=(96, 72))
 ref = None
-for fine_k, entry in T.CONFIGS:
-    out = T.run_kernels(poh, w, range(3), 1, fine_k, entry, grid=3)
+for brick, entry in T.CONFIGS:
+    out = T.run_kernels(poh, w, range(3), 1, brick, entry, grid=3)
     if ref is None:
         ref = out
     assert np.array_equal(out["hit"], ref["hit"]) and np.array_equal(out["bits"], ref["bits"])
 w["init_pos"][1] = np.array([1.0e6, 0.0, 0.0])
-T.run_kernels(poh, w, range(3), 1, 0, 0, max_range=0.3)          # literal march, a view out of the map
-T.run_kernels(poh, w, range(2), 0, 1, 1)                          # voxel mode (masked cull, gather)
+T.run_kernels(poh, w, range(3), 1, 8, 0, max_range=0.3)          # literal march, a view out of the map
+T.run_kernels(poh, w, range(2), 0, 4, 1)                          # voxel mode (masked region queue, gather)
 xyz = np.ascontiguousarray(w["cloud"][::8], dtype=np.float32)
 rgb = np.ascontiguousarray(w["cloud_rgb"][::8], dtype=np.uint8)
 pw = np.ascontiguousarray(w["pose_world"][:2], dtype=np.float64)
