@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprv_b200.so")
+LIB_PATH = os.environ.get("PRV_B200_LIB") or os.path.join(_HERE, "libprv_b200.so")  # (PRV_B200_LIB: A/B builds of tools/ab_build.sh)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "prv.h")
 
 NONE = 0xFFFFFFFF

@@ -67,7 +67,7 @@ __device__ __forceinline__ void write_hit(const CastParams& p, const ViewConst& 
 // kernel 3 (march_kernel):  dense warps over queue 2, the exact castRay march
 // Kernels 2 and 3 are persistent: kernel 2's blocks pull 256-pixel row-tiles, kernel 3's warps 32-ray chunks of a flattened
 // (view, chunk) list with an atomic ticket, so expensive and cheap chunks balance across the 148 SMs and there is no
-// partial last wave.  Both compact their survivors per warp (one atomic per warp).
+// partial last wave.
 
 // One block per kCullRegions consecutive 32x32-pixel regions of one row of one view (blockIdx = (region group, region
 // row, view)): the view constants are fetched once and the region tests of the group run side by side (one warp each),
@@ -183,30 +183,42 @@ template <int MINB, bool MASKED>
 __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
     __shared__ ViewConst s_vc;
     __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
-    __shared__ uint32_t s_ticket[2], s_vl[2];  // double-buffered: ONE block barrier per tile (the survivors are appended per warp)
-    if (threadIdx.x == 0) s_vl[1] = 0;
+    // Two block barriers per tile.  The ticket of the next tile is fetched by thread 0 while the block works on this one and is
+    // published by this tile's barriers (double-buffered slots); the survivors of a tile are appended to queue 2 as ONE run in
+    // warp order, with one atomic per tile.  (Round 2 measured per-warp appends -- one barrier per tile, one atomic per warp:
+    // coarse_kernel -2 %, but the runs of different blocks interleave in the queue, a 32-ray chunk of the march is no longer
+    // one 8x4 pixel patch, and march_kernel lost 13 % on C2 / 19 % on C3 to divergence: profiles/r2_march_ab.md.)
+    __shared__ uint32_t s_ticket[2], s_vl[2], s_wcnt[2][8], s_base[2][8];
     build_chunk_prefix(p.qcount + p.view_base, p.nviews, s_prefix, 256u, 4u);
     const uint32_t total = s_prefix[p.nviews];
     uint32_t cur_view = 0xFFFFFFFFu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        const uint32_t t = atomicAdd(p.tickets + 0, 1u);
+        uint32_t v = 0;
+        if (t < total)
+            while (s_prefix[v + 1] <= t) v++;
+        s_ticket[0] = t;
+        s_vl[0] = v;
+    }
+    __syncthreads();
     for (uint32_t it = 0;; it++) {
         const uint32_t slot = it & 1u;
-        if (threadIdx.x == 0) {
-            const uint32_t t = atomicAdd(p.tickets + 0, 1u);
-            s_ticket[slot] = t;
-            uint32_t v = s_vl[slot ^ 1u];
-            if (t < total)
-                while (s_prefix[v + 1] <= t) v++;  // tickets grow monotonically within a block: amortised O(1)
-            s_vl[slot] = v;
-        }
-        __syncthreads();  // (every warp has finished the previous tile: s_vc and the other ticket slot may be rewritten)
         const uint32_t g = s_ticket[slot];
         if (g >= total) break;
         const uint32_t vl = s_vl[slot];
         const uint32_t view = vl + p.view_base;
-        if (view != cur_view) {
+        if (view != cur_view) {  // (every warp passed the previous tile's second barrier: s_vc is no longer read)
             load_view_prefix(s_vc, p.views + view);
             cur_view = view;
+        }
+        if (threadIdx.x == 0) {  // next tile's ticket: its round trip overlaps this tile's work
+            const uint32_t t = atomicAdd(p.tickets + 0, 1u);
+            uint32_t v = vl;
+            if (t < total)
+                while (s_prefix[v + 1] <= t) v++;  // tickets grow monotonically within a block: amortised O(1)
+            s_ticket[slot ^ 1u] = t;
+            s_vl[slot ^ 1u] = v;
         }
         const ViewConst& vc = s_vc;
         // chunk = one 32x8 row-tile of a queued region; a warp covers an 8x4 patch of it
@@ -242,17 +254,31 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
         if (MASKED) {
             const uint32_t nact = __popc(__ballot_sync(0xFFFFFFFFu, active));
             if (lane == 0 && nact) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)nact);
-        } else if (threadIdx.x == 0) {
+        } else if (threadIdx.x == 32) {
             const int w = min(32, p.GW - x0), h = min(8, p.GH - y0);
             if (w > 0 && h > 0) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)(w * h));
         }
-        // survivors -> queue 2 (+ entry brick), compacted per warp: one atomic per warp, no block barrier
+        // survivors -> queue 2 (+ entry brick): one run per tile, warp after warp
         const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
-        uint32_t base = 0;
-        if (lane == 0 && bal) base = atomicAdd(p.qcount2 + view, (uint32_t)__popc(bal));
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (lane == 0) s_wcnt[slot][warp] = (uint32_t)__popc(bal);
+        __syncthreads();
+        if (warp == 0) {  // exclusive scan of the eight warp counts, one atomic for the tile
+            const uint32_t n = lane < 8 ? s_wcnt[slot][lane] : 0u;
+            uint32_t incl = n;
+#pragma unroll
+            for (int o = 1; o < 8; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 7);
+            uint32_t base = 0;
+            if (lane == 0 && tot) base = atomicAdd(p.qcount2 + view, tot);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (lane < 8) s_base[slot][lane] = base + incl - n;
+        }
+        __syncthreads();
         if (keep) {
-            const size_t pos = (size_t)view * p.queue_cap + base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+            const size_t pos = (size_t)view * p.queue_cap + s_base[slot][warp] + (uint32_t)__popc(bal & ((1u << lane) - 1u));
             p.queue2[pos] = pid;
             if (p.queue2b) p.queue2b[pos] = cell;
         }
@@ -268,11 +294,6 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
 // r2_staging_ab.md): 9 blocks of 128 threads (36 warps, 56 registers, 16 B spilled) +1 %, two probes in flight instead of
 // four +2 % on C2 / -0.5 % on C3.
 constexpr int kMarchBlock = 256, kMarchMinBlocks = 4;
-#ifndef PRVK_HOST_CHECK
-extern __shared__ uint32_t s_dyn_pad[];  // SMEM variant: the shell-padded occupancy bitmap, staged once per block
-#else
-static uint32_t* const s_dyn_pad = nullptr;  // (the CPU checker runs the default variant)
-#endif
 template <int BS, int MINB, bool SMEM = false>
 __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
     __shared__ ViewConst s_vcw[BS / 32];
@@ -330,7 +351,7 @@ __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
                     march_plain(p.map, p.cam, vc, r, res);
                     break;
                 }
-                if (march_axis<SMEM>(p.map, vc, r, cell, res, s_dyn_pad)) break;
+                if (march_axis<SMEM>(p.map, vc, r, cell, res)) break;
                 cell = kNone;
             }
             write_hit(p, vc, view, pid, res);
@@ -379,6 +400,16 @@ __global__ void __launch_bounds__(256) raycast_kernel(const CastParams p) {
     }
     if (in_grid && (!MASKED || active)) write_hit(p, vc, view, pid, res);
     commit_stats(p.stats + 4 * (size_t)view, active ? 1u : 0u, res.probes, res.rank != kNone ? 1u : 0u, res.steps);
+}
+
+// rs2_deproject_pixel_to_point of every integer pixel of the (W+1) x (H+1) grid at depth 1 (models 0 / 2 / 4), with the very
+// function the march would otherwise evaluate per ray: DevCam::deproj_exact
+__global__ void __launch_bounds__(256) deproj_table_kernel(DevCam cam, float2* out) {
+    const int px = blockIdx.x * 32 + (threadIdx.x & 31), py = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (px > cam.W || py > cam.H) return;
+    float x, y;
+    deproject_pixel(cam, (float)px, (float)py, x, y);
+    out[(size_t)py * (size_t)(cam.W + 1) + (size_t)px] = make_float2(x, y);
 }
 
 // voxel-driven mode, stage 1 (main.cpp:243-251 of the reference): project every occupied voxel centre, mark its

@@ -1160,6 +1160,7 @@ int prv_set_camera(prv_ctx* ctx, const prv_intrinsics* intr, double max_range) {
         const bool ok = !transcendental && region_cull_valid(*intr);
         ctx->cam.region_cull_ok = ok ? 1 : 0;
         ctx->cam.deproj_table = nullptr;
+        ctx->cam.deproj_exact = nullptr;
         if (transcendental) {
             // F-Theta / Kannala-Brandt: tan / atan are the host libm's (as in the reference built on this host), so the
             // deprojection of every integer pixel is tabulated here and the kernels only read it
@@ -1181,7 +1182,22 @@ int prv_set_camera(prv_ctx* ctx, const prv_intrinsics* intr, double max_range) {
             CU(h2d(ctx, ctx->d_deproj.p, tab.data(), tab.size() * 4));
             CU(cudaStreamSynchronize(ctx->stream));
             ctx->cam.deproj_table = ptr<float2>(ctx->d_deproj);
+            ctx->cam.deproj_exact = ctx->cam.deproj_table;
             PRV_GUARD_END(ctx, "prv_set_camera")
+        } else {
+            const char* e = getenv("PRV_DEPROJ_TABLE");  // A/B switch: 0 = the march evaluates deproject_pixel per ray
+            if (!(e && e[0] == '0')) {
+                CU(cudaSetDevice(ctx->device));
+                CU(join_score(ctx));
+                const size_t GW = (size_t)intr->width + 1, GH = (size_t)intr->height + 1;
+                int rc;
+                if ((rc = ensure(ctx, ctx->d_deproj, GW * GH * 8))) return rc;
+                DevCam cam = ctx->cam;
+                cam.deproj_exact = nullptr;
+                deproj_table_kernel<<<dim3((unsigned)((GW + 31) / 32), (unsigned)((GH + 7) / 8)), 256, 0, ctx->stream>>>(cam, ptr<float2>(ctx->d_deproj));
+                CU(cudaGetLastError());
+                ctx->cam.deproj_exact = ptr<float2>(ctx->d_deproj);
+            }
         }
         ctx->intr_checked = *intr;
     }

@@ -32,6 +32,7 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __fdividef(float a, float b) { return a / b; }  // culls only
 static inline float rsqrtf(float a) { return 1.0f / std::sqrt(a); }  // culls only
@@ -55,7 +56,9 @@ using std::min;
 // ---- dda_step: the one function of the header written in PTX; same statement in C++ ------------------------------------
 #define PRVK_HOST_CHECK 1
 namespace prvk {
-static inline uint32_t dda_step(double& t0, double& t1, double& t2, double d0, double d1, double d2, uint32_t inc0, uint32_t inc1, uint32_t inc2) {
+struct DdaMasks;
+static inline void dda_masks_init(DdaMasks&) {}
+static inline uint32_t dda_step(double& t0, double& t1, double& t2, double d0, double d1, double d2, uint32_t inc0, uint32_t inc1, uint32_t inc2, DdaMasks&) {
     const bool c01 = t0 < t1, c02 = t0 < t2, c12 = t1 < t2;
     const bool p0 = c01 && c02, p1 = !c01 && c12, p2 = !(p0 || p1);
     t0 = std::fma(p0 ? 1.0 : 0.0, d0, t0);

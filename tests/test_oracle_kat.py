@@ -246,6 +246,18 @@ def test_exact_skip_ahead_of_the_tmax_recurrence_matches_the_literal_loop(tmp_pa
     assert r.returncode == 0 and "mismatches 0" in r.stdout, r.stdout[-2000:]
 
 
+def test_float_sqrt_equals_double_sqrt_rounded_to_float_for_every_float(tmp_path):
+    """tests/cpp/test_sqrt_rounding.cpp: octomath's norm() is `(float)sqrt((double)norm_sq)`; the march takes it with one
+    correctly rounded float square root.  Exhaustive over all non-negative floats."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "test_sqrt_rounding"
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([gxx, "-O2", "-fopenmp", "-ffp-contract=off", "-o", str(exe), os.path.join(root, "tests", "cpp", "test_sqrt_rounding.cpp")], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "mismatches: 0 of 2139095041" in r.stdout, r.stdout[-500:]
+
+
 def _py_cast_ray(occ, origin, dirp, res, max_range, ignore_unknown=True):
     """castRay of OctoMap 1.9.x written a second time, independently of oracle/prv_oracle.cpp, straight from the frozen
     spec in SURVEY.md section 8(c), with numpy scalars standing in for the C types (np.float32 = float, python float =
