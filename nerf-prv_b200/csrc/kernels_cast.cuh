@@ -294,6 +294,10 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
 // r2_staging_ab.md): 9 blocks of 128 threads (36 warps, 56 registers, 16 B spilled) +1 %, two probes in flight instead of
 // four +2 % on C2 / -0.5 % on C3.
 constexpr int kMarchBlock = 256, kMarchMinBlocks = 4;
+#ifndef PRV_MARCH_TICKET_MAX
+#define PRV_MARCH_TICKET_MAX 8
+#endif
+constexpr int kMarchTicketMax = PRV_MARCH_TICKET_MAX;
 template <int BS, int MINB, bool SMEM = false>
 __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
     __shared__ ViewConst s_vcw[BS / 32];
@@ -304,6 +308,14 @@ __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
     }
     build_chunk_prefix(p.qcount2 + p.view_base, p.nviews, s_prefix, 32u);
     const uint32_t total = s_prefix[p.nviews];
+    // A ticket is `per` consecutive chunks of the flattened list: 1 for small casts (C2: 23 chunks per warp, balance matters), up to
+    // kMarchTicketMax when every warp still gets 64+ tickets -- on the 1024-view workload a warp that takes single chunks changes
+    // view (constants reloaded, counters flushed) on four chunks out of five (C3 march 12.07 -> 11.66 ms; C2 0.424 -> 0.537 ms if
+    // forced there, profiles/r2_march_ab.md).  Every block derives the same value from the same table.
+    // (kept in shared memory and re-read per ticket: two more live registers put MOVs back into the four-probe loop)
+    __shared__ uint32_t s_per;
+    if (threadIdx.x == 0) s_per = min((uint32_t)kMarchTicketMax, max(1u, total / (gridDim.x * (uint32_t)(BS / 32) * 64u)));
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ViewConst& vc = s_vcw[warp];
     uint32_t cur_view = 0xFFFFFFFFu;
@@ -312,10 +324,15 @@ __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
     uint32_t next = 0;
     if (lane == 0) next = atomicAdd(p.tickets + 1, 1u);
     next = __shfl_sync(0xFFFFFFFFu, next, 0);
-    while (next < total) {
-        const uint32_t g = next;
-        if (lane == 0) next = atomicAdd(p.tickets + 1, 1u);  // consumed after this chunk: the round trip overlaps the march
-        while (s_prefix[vl + 1] <= g) vl++;                  // a warp's tickets grow monotonically: amortised O(1)
+    for (;;) {
+        const uint32_t per = *reinterpret_cast<volatile uint32_t*>(&s_per);
+        uint32_t g = next * per;
+        if (g >= s_prefix[p.nviews]) break;
+        const uint32_t g_end = min(s_prefix[p.nviews], g + per);
+        if (lane == 0) next = atomicAdd(p.tickets + 1, 1u);  // consumed after this ticket: the round trip overlaps the march
+#pragma unroll 1
+        for (; g < g_end; g++) {
+        while (s_prefix[vl + 1] <= g) vl++;                  // a warp's chunks grow monotonically: amortised O(1)
         const uint32_t view = vl + p.view_base;
         if (view != cur_view) {
             if (cur_view != 0xFFFFFFFFu) {  // flush the finished view's counters: one atomic per counter per (warp, view)
@@ -358,6 +375,7 @@ __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
             c_probes += res.probes;
             c_hits += res.rank != kNone ? 1u : 0u;
             c_steps += res.steps;
+        }
         }
         next = __shfl_sync(0xFFFFFFFFu, next, 0);
     }
