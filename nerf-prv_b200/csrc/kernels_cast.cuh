@@ -191,10 +191,13 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
     __shared__ uint32_t s_ticket[2], s_vl[2], s_wcnt[2][8], s_base[2][8];
     build_chunk_prefix(p.qcount + p.view_base, p.nviews, s_prefix, 256u, 4u);
     const uint32_t total = s_prefix[p.nviews];
+    // A ticket is one row-tile, or -- when every block still gets 64+ tickets -- the four row-tiles of a region (the 1024-view
+    // workload: a block that takes single tiles changes view on most of them).  A view's tiles start at a multiple of four.
+    const uint32_t per = total / (gridDim.x * 64u) >= 4u ? 4u : 1u;
     uint32_t cur_view = 0xFFFFFFFFu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        const uint32_t t = atomicAdd(p.tickets + 0, 1u);
+        const uint32_t t = atomicAdd(p.tickets + 0, 1u) * per;
         uint32_t v = 0;
         if (t < total)
             while (s_prefix[v + 1] <= t) v++;
@@ -202,24 +205,26 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
         s_vl[0] = v;
     }
     __syncthreads();
-    for (uint32_t it = 0;; it++) {
-        const uint32_t slot = it & 1u;
-        const uint32_t g = s_ticket[slot];
-        if (g >= total) break;
-        const uint32_t vl = s_vl[slot];
+    for (uint32_t it = 0, tile_no = 0;; it++) {
+        const uint32_t tslot = it & 1u;
+        const uint32_t g0 = s_ticket[tslot];
+        if (g0 >= total) break;
+        const uint32_t vl = s_vl[tslot];
         const uint32_t view = vl + p.view_base;
         if (view != cur_view) {  // (every warp passed the previous tile's second barrier: s_vc is no longer read)
             load_view_prefix(s_vc, p.views + view);
             cur_view = view;
         }
-        if (threadIdx.x == 0) {  // next tile's ticket: its round trip overlaps this tile's work
-            const uint32_t t = atomicAdd(p.tickets + 0, 1u);
+        if (threadIdx.x == 0) {  // next ticket: its round trip overlaps this one's work
+            const uint32_t t = atomicAdd(p.tickets + 0, 1u) * per;
             uint32_t v = vl;
             if (t < total)
                 while (s_prefix[v + 1] <= t) v++;  // tickets grow monotonically within a block: amortised O(1)
-            s_ticket[slot ^ 1u] = t;
-            s_vl[slot ^ 1u] = v;
+            s_ticket[tslot ^ 1u] = t;
+            s_vl[tslot ^ 1u] = v;
         }
+        for (uint32_t g = g0; g < g0 + per; g++, tile_no++) {
+        const uint32_t slot = tile_no & 1u;
         const ViewConst& vc = s_vc;
         // chunk = one 32x8 row-tile of a queued region; a warp covers an 8x4 patch of it
         const uint32_t c = g - s_prefix[vl];
@@ -281,6 +286,7 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
             const size_t pos = (size_t)view * p.queue_cap + s_base[slot][warp] + (uint32_t)__popc(bal & ((1u << lane) - 1u));
             p.queue2[pos] = pid;
             if (p.queue2b) p.queue2b[pos] = cell;
+        }
         }
     }
 }
