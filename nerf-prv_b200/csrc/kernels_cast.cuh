@@ -177,27 +177,121 @@ __device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint3
     __syncthreads();
 }
 
-// Persistent blocks over the (view, region row-tile) list: per pixel the approximate direction and the conservative brick walk
+// Persistent WARPS over the (view, region row-tile) list: per pixel the approximate direction and the conservative brick walk
 // (coarse_miss; its own slab test against the AABB grown by one voxel is the first thing it does).  Survivors -> queue 2.
-template <int MINB, bool MASKED>
-__global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
+// A warp takes a whole 32x8 row-tile (or the four row-tiles of a region, when every warp still gets 64+ tickets: on the 1024-view
+// workload a warp that takes single tiles changes view on most of them), walks its eight 8x4 pixel patches one after the other,
+// collects the survivors in its own 256-entry shared-memory stage and appends them to queue 2 as ONE run per tile with one atomic
+// -- no block barrier after the chunk-prefix table is built.  Round 2 went through three forms of this kernel
+// (profiles/r2_march_ab.md): blocks of eight warps per tile with a block-wide compaction (2-4 barriers per tile: ~30 % of the
+// kernel's stall samples sat at those barriers); per-warp appends of single patches (no barriers, but the runs of different
+// blocks interleave in the queue, a 32-ray chunk of the march is no longer one patch, and march_kernel lost 13 % on C2 / 19 % on
+// C3 to divergence); and this one, which keeps the run-per-tile order of the first and the independence of the second (C3 cull +
+// coarse 5.34 -> 4.95 ms).  A warp needs a tile's time for its last ticket, though: with few tiles per warp (C2: 3.5) the tail costs
+// more than the barriers did (C2 0.190 -> 0.222 ms), so small casts keep the block form -- coarse_kernel picks by the tile count.
+constexpr int kCoarseStage = 256;
+template <bool MASKED>
+__device__ __forceinline__ void coarse_tiles_by_warp(const CastParams& p, const uint32_t* s_prefix, const uint32_t total) {
+    __shared__ __align__(16) uint32_t s_vcw[8][kViewCullWords];  // the cull prefix of each warp's current view (96 B rows)
+    __shared__ uint32_t s_pid[8][kCoarseStage], s_cell[8][kCoarseStage];
+    const uint32_t per = total / (gridDim.x * 8u * 64u) >= 4u ? 4u : 1u;  // (a view's tiles start at a multiple of four)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const ViewConst& vc = *reinterpret_cast<const ViewConst*>(s_vcw[warp]);  // (prefix words only)
+    uint32_t* const stage_pid = s_pid[warp];
+    uint32_t* const stage_cell = s_cell[warp];
+    uint32_t cur_view = 0xFFFFFFFFu;
+    uint32_t vl = 0;
+    uint32_t next = 0;
+    if (lane == 0) next = atomicAdd(p.tickets + 0, 1u);
+    next = __shfl_sync(0xFFFFFFFFu, next, 0);
+    for (;;) {
+        const uint32_t g0 = next * per;
+        if (g0 >= total) break;
+        if (lane == 0) next = atomicAdd(p.tickets + 0, 1u);  // consumed after this ticket: the round trip overlaps the walk
+        while (s_prefix[vl + 1] <= g0) vl++;                 // a warp's tickets grow monotonically: amortised O(1)
+        const uint32_t view = vl + p.view_base;
+        if (view != cur_view) {
+            __syncwarp();
+            if (lane < kViewCullWords) s_vcw[warp][lane] = reinterpret_cast<const uint32_t*>(p.views + view)[lane];
+            __syncwarp();
+            cur_view = view;
+        }
+#pragma unroll 1
+        for (uint32_t g = g0; g < g0 + per; g++) {
+            // one 32x8 row-tile of a queued region, as eight 8x4 patches
+            const uint32_t c = g - s_prefix[vl];
+            const uint32_t region = p.queue[(size_t)view * p.rqueue_cap + (c >> 2)];
+            const int x0 = (int)((region & 0xFFFFu) << 5), y0 = (int)((region >> 16) << 5) + (int)((c & 3u) << 3);
+            uint32_t n = 0, nrays = 0;
+#pragma unroll 1
+            for (int patch = 0; patch < 8; patch++) {
+                const int px = x0 + ((patch & 3) << 3) + (lane & 7);
+                const int py = y0 + ((patch >> 2) << 2) + (lane >> 3);
+                bool active = px < p.GW && py < p.GH;
+                if (MASKED && active) {
+                    const unsigned long long lin = (unsigned long long)py * p.GW + px;
+                    const uint32_t w = __ldg(p.mask + (size_t)view * p.mask_words + (uint32_t)(lin >> 5));
+                    active = (w >> (lin & 31)) & 1u;
+                }
+                bool keep = false;
+                uint32_t cell = kNone;
+                if (active) {
+                    if (!(vc.flags & kViewFastOk)) {
+                        keep = true;  // this view needs the literal march (max-range test): no cull
+                    } else {
+                        float dx, dy, dz;
+                        ray_direction_approx_px(p.cam, vc, px, py, dx, dy, dz);
+                        keep = !coarse_miss(p.map, vc, dx, dy, dz, cell);
+                    }
+                    if (!keep && p.pix_hit) {
+                        const size_t o = (size_t)view * p.pix_stride + (size_t)py * p.GW + px;
+                        p.pix_hit[o] = kNone;
+                        if (p.pix_depth) p.pix_depth[o] = 0.0f;
+                    }
+                }
+                if (MASKED) nrays += __popc(__ballot_sync(0xFFFFFFFFu, active));
+                const uint32_t bal = __ballot_sync(0xFFFFFFFFu, keep);
+                if (keep) {
+                    const uint32_t i = n + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                    stage_pid[i] = ((uint32_t)py << 16) | (uint32_t)px;  // queues carry (y,x) packed: no division downstream
+                    stage_cell[i] = cell;
+                }
+                n += (uint32_t)__popc(bal);
+            }
+            if (!MASKED) nrays = (uint32_t)(max(0, min(32, p.GW - x0)) * max(0, min(8, p.GH - y0)));  // dense mode: by geometry
+            __syncwarp();
+            // the tile's survivors -> queue 2 (+ entry brick): one run, one atomic
+            uint32_t base = 0;
+            if (lane == 0) {
+                if (nrays) atomicAdd(p.stats + 4 * (size_t)view, (unsigned long long)nrays);
+                if (n) base = atomicAdd(p.qcount2 + view, n);
+            }
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            for (uint32_t i = (uint32_t)lane; i < n; i += 32u) {
+                const size_t pos = (size_t)view * p.queue_cap + base + i;
+                p.queue2[pos] = stage_pid[i];
+                if (p.queue2b) p.queue2b[pos] = stage_cell[i];
+            }
+            __syncwarp();  // (the stage is rewritten by the next tile)
+        }
+        next = __shfl_sync(0xFFFFFFFFu, next, 0);
+    }
+}
+
+template <bool MASKED>
+__device__ __forceinline__ void coarse_tiles_by_block(const CastParams& p, const uint32_t* s_prefix, const uint32_t total) {
     __shared__ ViewConst s_vc;
-    __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
-    // Two block barriers per tile.  The ticket of the next tile is fetched by thread 0 while the block works on this one and is
+    // Small casts (a few tiles per warp: C2 has 3.5): the eight warps of a block share a tile, one 8x4 patch each, so that the tail of
+    // the kernel is a patch long, not a tile.  Two block barriers per tile.  The ticket of the next tile is fetched by thread 0 while the block works on this one and is
     // published by this tile's barriers (double-buffered slots); the survivors of a tile are appended to queue 2 as ONE run in
     // warp order, with one atomic per tile.  (Round 2 measured per-warp appends -- one barrier per tile, one atomic per warp:
     // coarse_kernel -2 %, but the runs of different blocks interleave in the queue, a 32-ray chunk of the march is no longer
     // one 8x4 pixel patch, and march_kernel lost 13 % on C2 / 19 % on C3 to divergence: profiles/r2_march_ab.md.)
     __shared__ uint32_t s_ticket[2], s_vl[2], s_wcnt[2][8], s_base[2][8];
-    build_chunk_prefix(p.qcount + p.view_base, p.nviews, s_prefix, 256u, 4u);
-    const uint32_t total = s_prefix[p.nviews];
-    // A ticket is one row-tile, or -- when every block still gets 64+ tickets -- the four row-tiles of a region (the 1024-view
-    // workload: a block that takes single tiles changes view on most of them).  A view's tiles start at a multiple of four.
-    const uint32_t per = total / (gridDim.x * 64u) >= 4u ? 4u : 1u;
     uint32_t cur_view = 0xFFFFFFFFu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        const uint32_t t = atomicAdd(p.tickets + 0, 1u) * per;
+        const uint32_t t = atomicAdd(p.tickets + 0, 1u);
         uint32_t v = 0;
         if (t < total)
             while (s_prefix[v + 1] <= t) v++;
@@ -205,26 +299,24 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
         s_vl[0] = v;
     }
     __syncthreads();
-    for (uint32_t it = 0, tile_no = 0;; it++) {
-        const uint32_t tslot = it & 1u;
-        const uint32_t g0 = s_ticket[tslot];
-        if (g0 >= total) break;
-        const uint32_t vl = s_vl[tslot];
+    for (uint32_t it = 0;; it++) {
+        const uint32_t slot = it & 1u;
+        const uint32_t g = s_ticket[slot];
+        if (g >= total) break;
+        const uint32_t vl = s_vl[slot];
         const uint32_t view = vl + p.view_base;
         if (view != cur_view) {  // (every warp passed the previous tile's second barrier: s_vc is no longer read)
             load_view_prefix(s_vc, p.views + view);
             cur_view = view;
         }
-        if (threadIdx.x == 0) {  // next ticket: its round trip overlaps this one's work
-            const uint32_t t = atomicAdd(p.tickets + 0, 1u) * per;
+        if (threadIdx.x == 0) {  // next tile's ticket: its round trip overlaps this tile's work
+            const uint32_t t = atomicAdd(p.tickets + 0, 1u);
             uint32_t v = vl;
             if (t < total)
                 while (s_prefix[v + 1] <= t) v++;  // tickets grow monotonically within a block: amortised O(1)
-            s_ticket[tslot ^ 1u] = t;
-            s_vl[tslot ^ 1u] = v;
+            s_ticket[slot ^ 1u] = t;
+            s_vl[slot ^ 1u] = v;
         }
-        for (uint32_t g = g0; g < g0 + per; g++, tile_no++) {
-        const uint32_t slot = tile_no & 1u;
         const ViewConst& vc = s_vc;
         // chunk = one 32x8 row-tile of a queued region; a warp covers an 8x4 patch of it
         const uint32_t c = g - s_prefix[vl];
@@ -287,8 +379,19 @@ __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
             p.queue2[pos] = pid;
             if (p.queue2b) p.queue2b[pos] = cell;
         }
-        }
     }
+}
+
+constexpr uint32_t kCoarseWarpTiles = 32;  // tiles per warp from which the warps work on their own
+template <int MINB, bool MASKED>
+__global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
+    __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
+    build_chunk_prefix(p.qcount + p.view_base, p.nviews, s_prefix, 256u, 4u);
+    const uint32_t total = s_prefix[p.nviews];
+    if (total >= gridDim.x * 8u * kCoarseWarpTiles)
+        coarse_tiles_by_warp<MASKED>(p, s_prefix, total);
+    else
+        coarse_tiles_by_block<MASKED>(p, s_prefix, total);
 }
 
 // Persistent WARPS: every warp pulls 32-ray chunks of the flattened (view, chunk) list with its own atomic ticket and

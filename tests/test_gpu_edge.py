@@ -99,7 +99,7 @@ def test_coarse_resolution_and_unlimited_range(prv, orc, synth, ctx):
 
 
 def test_more_views_than_one_launch_batch(prv, orc, synth, ctx):
-    """2100 views > kMaxViewsPerLaunch (2048): the persistent kernels run in two view batches."""
+    """2100 views > kMaxViewsPerLaunch (1024): the persistent kernels run in three view batches."""
     w = synth.build_workload(prv, "C1", n_views=100, size=(24, 16))
     reps = 21
     pw = np.concatenate([w["pose_world"]] * reps)
