@@ -189,12 +189,21 @@ __device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint3
 // C3 to divergence); and this one, which keeps the run-per-tile order of the first and the independence of the second (C3 cull +
 // coarse 5.34 -> 4.95 ms).  A warp needs a tile's time for its last ticket, though: with few tiles per warp (C2: 3.5) the tail costs
 // more than the barriers did (C2 0.190 -> 0.222 ms), so small casts keep the block form -- coarse_kernel picks by the tile count.
+#ifndef PRV_COARSE_WARP_TILES
+#define PRV_COARSE_WARP_TILES 32
+#endif
+#ifndef PRV_TICKET_SPREAD
+#define PRV_TICKET_SPREAD 64  // tickets every warp must still get before a ticket grows beyond one tile / one chunk
+#endif
+// (both overridable so that the CPU checker can force the large-cast paths on its small scenes: tests/test_kernel_on_host.py)
+constexpr uint32_t kCoarseWarpTiles = PRV_COARSE_WARP_TILES;  // tiles per warp from which the warps work on their own
+constexpr uint32_t kTicketSpread = PRV_TICKET_SPREAD;
 constexpr int kCoarseStage = 256;
 template <bool MASKED>
 __device__ __forceinline__ void coarse_tiles_by_warp(const CastParams& p, const uint32_t* s_prefix, const uint32_t total) {
     __shared__ __align__(16) uint32_t s_vcw[8][kViewCullWords];  // the cull prefix of each warp's current view (96 B rows)
     __shared__ uint32_t s_pid[8][kCoarseStage], s_cell[8][kCoarseStage];
-    const uint32_t per = total / (gridDim.x * 8u * 64u) >= 4u ? 4u : 1u;  // (a view's tiles start at a multiple of four)
+    const uint32_t per = total / (gridDim.x * 8u * kTicketSpread) >= 4u ? 4u : 1u;  // (a view's tiles start at a multiple of four)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ViewConst& vc = *reinterpret_cast<const ViewConst*>(s_vcw[warp]);  // (prefix words only)
     uint32_t* const stage_pid = s_pid[warp];
@@ -382,7 +391,7 @@ __device__ __forceinline__ void coarse_tiles_by_block(const CastParams& p, const
     }
 }
 
-constexpr uint32_t kCoarseWarpTiles = 32;  // tiles per warp from which the warps work on their own
+
 template <int MINB, bool MASKED>
 __global__ void __launch_bounds__(256, MINB) coarse_kernel(const CastParams p) {
     __shared__ uint32_t s_prefix[kMaxViewsPerLaunch + 1];
@@ -423,7 +432,7 @@ __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
     // forced there, profiles/r2_march_ab.md).  Every block derives the same value from the same table.
     // (kept in shared memory and re-read per ticket: two more live registers put MOVs back into the four-probe loop)
     __shared__ uint32_t s_per;
-    if (threadIdx.x == 0) s_per = min((uint32_t)kMarchTicketMax, max(1u, total / (gridDim.x * (uint32_t)(BS / 32) * 64u)));
+    if (threadIdx.x == 0) s_per = min((uint32_t)kMarchTicketMax, max(1u, total / (gridDim.x * (uint32_t)(BS / 32) * kTicketSpread)));
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const ViewConst& vc = s_vcw[warp];

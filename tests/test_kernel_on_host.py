@@ -445,6 +445,19 @@ def poh(tmp_path_factory):
     return C.CDLL(str(out))
 
 
+FORCE_LARGE_CAST_PATHS = ["-DPRV_COARSE_WARP_TILES=0", "-DPRV_TICKET_SPREAD=1"]  # warps on whole tiles, region tickets, multi-chunk march tickets
+
+
+@pytest.fixture(scope="module")
+def poh_large(tmp_path_factory):
+    """The same kernels with the thresholds that switch to the large-cast paths (kernels_cast.cuh) set to "always"."""
+    out = tmp_path_factory.mktemp("pohl") / "libpipeline_on_host_large.so"
+    gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.run([gxx, "-O2", "-std=c++20", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC", "-pthread", "-I/usr/local/cuda/include"] + FORCE_LARGE_CAST_PATHS +
+                   ["-o", str(out), os.path.join(ROOT, "tests", "cpp", "pipeline_on_host.cpp")], check=True)
+    return C.CDLL(str(out))
+
+
 CONFIGS = ((8, 1), (8, 0), (4, 1))  # (brick edge, enter at brick): the default pipeline, the march from the AABB face, smaller bricks
 
 
@@ -486,6 +499,19 @@ def test_cast_kernels_on_the_emulator_match_oracle(poh, koh, prv, orc, synth, na
             _, _, st = cast_dense(koh, w, v, 2, brick=brick, entry=bool(entry))  # the per-ray check counts the same work
             assert out["stats"][v].tolist() == [st["rays"], st["probes"], st["hits"], st["steps"]] and out["marched"][v] == st["marched"]
             assert st["hits"] == o_st["hits"]
+
+
+@pytest.mark.parametrize("name,size,grid,mode", [("C1", (96, 72), 1, 1), ("C2", (97, 61), 2, 1), ("C1", (160, 120), 1, 0)])
+def test_large_cast_paths_on_the_emulator_match_the_default_paths(poh, poh_large, prv, synth, name, size, grid, mode):
+    """coarse_kernel with every warp walking whole tiles on its own (region tickets) and march_kernel with tickets of several
+    chunks -- the forms the 1024-view workload runs -- give what the small-cast forms give, counters included."""
+    w = synth.build_workload(prv, name, n_views=3, size=size)
+    for brick, entry in ((8, 1), (4, 0)):
+        a = run_kernels(poh, w, range(3), mode, brick, entry, grid)
+        b = run_kernels(poh_large, w, range(3), mode, brick, entry, grid)
+        for k in ("hit", "depth", "bits", "stats", "marched", "voxel_hit"):
+            assert np.array_equal(a[k], b[k]), (k, brick, entry)
+        assert int(b["marched"].sum()) > 0
 
 
 def test_cast_kernels_on_the_emulator_full_size_view(poh, prv, synth):
@@ -576,7 +602,8 @@ def test_ensemble_kernels_on_the_emulator(poh, orc, method, E):
     assert np.array_equal(scores, o_scores)
 
 
-def test_kernels_are_race_free_under_threadsanitizer(tmp_path):
+@pytest.mark.parametrize("flags", [[], FORCE_LARGE_CAST_PATHS], ids=["small-cast paths", "large-cast paths"])
+def test_kernels_are_race_free_under_threadsanitizer(tmp_path, flags):
     """The emulator runs CUDA threads as real concurrent OS threads synchronised only by the kernels' own barriers, warp
     collectives and atomics -- so ThreadSanitizer sees what compute-sanitizer's racecheck sees on the device, and more (global
     memory too).  The cull / coarse / march / voxel-mode / splat kernels must run without a single report; the one suppressed
@@ -586,8 +613,9 @@ def test_kernels_are_race_free_under_threadsanitizer(tmp_path):
     if not os.path.isabs(tsan) or not os.path.exists(tsan):
         pytest.skip("libtsan not installed")
     lib = tmp_path / "libpipeline_on_host_tsan.so"
-    subprocess.run([gxx, "-O1", "-g", "-std=c++20", "-ffp-contract=off", "-fsanitize=thread", "-shared", "-fPIC", "-pthread", "-I/usr/local/cuda/include",
-                    "-o", str(lib), os.path.join(ROOT, "tests", "cpp", "pipeline_on_host.cpp")], check=True)
+    # (both forms of coarse_kernel / of the tickets: the block barriers of the small casts, the shared-memory stage and per-warp tickets of the large ones)
+    subprocess.run([gxx, "-O1", "-g", "-std=c++20", "-ffp-contract=off", "-fsanitize=thread", "-shared", "-fPIC", "-pthread", "-I/usr/local/cuda/include"] +
+                   flags + ["-o", str(lib), os.path.join(ROOT, "tests", "cpp", "pipeline_on_host.cpp")], check=True)
     env = dict(os.environ, LD_PRELOAD=tsan,
                TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 history_size=2 suppressions=" + os.path.join(ROOT, "tests", "tsan", "suppressions.txt"))
     import sys
