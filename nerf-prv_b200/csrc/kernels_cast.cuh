@@ -179,7 +179,7 @@ __device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint3
 
 // Persistent WARPS over the (view, region row-tile) list: per pixel the approximate direction and the conservative brick walk
 // (coarse_miss; its own slab test against the AABB grown by one voxel is the first thing it does).  Survivors -> queue 2.
-// A warp takes a whole 32x8 row-tile (or the four row-tiles of a region, when every warp still gets 64+ tickets: on the 1024-view
+// A warp takes a whole 32x8 row-tile (or the four row-tiles of a region, when every warp still gets 32+ tickets: on the 1024-view
 // workload a warp that takes single tiles changes view on most of them), walks its eight 8x4 pixel patches one after the other,
 // collects the survivors in its own 256-entry shared-memory stage and appends them to queue 2 as ONE run per tile with one atomic
 // -- no block barrier after the chunk-prefix table is built.  Round 2 went through three forms of this kernel
@@ -190,10 +190,10 @@ __device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint3
 // coarse 5.34 -> 4.95 ms).  A warp needs a tile's time for its last ticket, though: with few tiles per warp (C2: 3.5) the tail costs
 // more than the barriers did (C2 0.190 -> 0.222 ms), so small casts keep the block form -- coarse_kernel picks by the tile count.
 #ifndef PRV_COARSE_WARP_TILES
-#define PRV_COARSE_WARP_TILES 32
+#define PRV_COARSE_WARP_TILES 12
 #endif
 #ifndef PRV_TICKET_SPREAD
-#define PRV_TICKET_SPREAD 64  // tickets every warp must still get before a ticket grows beyond one tile / one chunk
+#define PRV_TICKET_SPREAD 32  // tickets every warp must still get before a ticket grows beyond one tile / one chunk
 #endif
 // (both overridable so that the CPU checker can force the large-cast paths on its small scenes: tests/test_kernel_on_host.py)
 constexpr uint32_t kCoarseWarpTiles = PRV_COARSE_WARP_TILES;  // tiles per warp from which the warps work on their own
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(BS, MINB) march_kernel(const CastParams p) {
     build_chunk_prefix(p.qcount2 + p.view_base, p.nviews, s_prefix, 32u);
     const uint32_t total = s_prefix[p.nviews];
     // A ticket is `per` consecutive chunks of the flattened list: 1 for small casts (C2: 23 chunks per warp, balance matters), up to
-    // kMarchTicketMax when every warp still gets 64+ tickets -- on the 1024-view workload a warp that takes single chunks changes
+    // kMarchTicketMax when every warp still gets 32+ tickets -- on the 1024-view workload a warp that takes single chunks changes
     // view (constants reloaded, counters flushed) on four chunks out of five (C3 march 12.07 -> 11.66 ms; C2 0.424 -> 0.537 ms if
     // forced there, profiles/r2_march_ab.md).  Every block derives the same value from the same table.
     // (kept in shared memory and re-read per ticket: two more live registers put MOVs back into the four-probe loop)
