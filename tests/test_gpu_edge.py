@@ -2,6 +2,7 @@
 the occupancy AABB, thin and single-voxel maps, coarse voxels, unlimited range, more views than one launch batch, and
 the error behaviour of the C ABI."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -321,3 +322,21 @@ def test_abi_guards_of_round_2(prv, synth):
         assert t["dropped"] == 0
     finally:
         c.close()
+
+
+@pytest.mark.gpu
+def test_shared_reciprocal_division_equals_ddiv_rn_bit_for_bit(tmp_path):
+    """ddiv_pair (prv_kernels.cuh): the two divisions of a castRay axis with one refined reciprocal, against __ddiv_rn on the GPU
+    -- 2^28 operand triples of the march's own ranges, 2^26 raw bit patterns (NaNs, infinities, denormals, zeros) and 2^26 with
+    exponents near the ends of the range (tests/cuda/test_ddiv_pair.cu, compiled here with nvcc)."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "test_ddiv_pair"
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-fmad=false", "-I", os.path.join(root, "nerf-prv_b200", "csrc"), "-I", os.path.join(root, "include"),
+                    "-o", str(exe), os.path.join(root, "tests", "cuda", "test_ddiv_pair.cu")], check=True, capture_output=True)
+    r = subprocess.run([str(exe), "26"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "mismatches: 0" in r.stdout, r.stdout[-2000:] + r.stderr[-500:]
