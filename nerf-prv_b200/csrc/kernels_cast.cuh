@@ -198,6 +198,10 @@ __device__ __forceinline__ void build_chunk_prefix(const uint32_t* counts, uint3
 // (both overridable so that the CPU checker can force the large-cast paths on its small scenes: tests/test_kernel_on_host.py)
 constexpr uint32_t kCoarseWarpTiles = PRV_COARSE_WARP_TILES;  // tiles per warp from which the warps work on their own
 constexpr uint32_t kTicketSpread = PRV_TICKET_SPREAD;
+#ifndef PRV_COARSE_MINB
+#define PRV_COARSE_MINB 8
+#endif
+constexpr int kCoarseMinBlocks = PRV_COARSE_MINB;  // resident blocks per SM the register budget is set for (8: 32 registers)
 constexpr int kCoarseStage = 256;
 template <bool MASKED>
 __device__ __forceinline__ void coarse_tiles_by_warp(const CastParams& p, const uint32_t* s_prefix, const uint32_t total) {

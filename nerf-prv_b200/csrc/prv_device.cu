@@ -539,7 +539,7 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels, bool publish = false) {
         if (ctx->variant == PRV_VARIANT_AXIS) {
             p.tickets = ctx->p_tickets + 2 * li;
             if (ctx->occ_coarse == 0) {  // persistent grids = exactly one resident wave
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_coarse, coarse_kernel<8, false>, 256, 0);
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_coarse, coarse_kernel<kCoarseMinBlocks, false>, 256, 0);
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_march, march_kernel<kMarchBlock, kMarchMinBlocks>, kMarchBlock, 0);
                 ctx->occ_coarse = std::max(1, ctx->occ_coarse);
                 ctx->occ_march = std::max(1, ctx->occ_march);
@@ -553,9 +553,9 @@ int cast_impl(prv_ctx* ctx, int mode, int want_pixels, bool publish = false) {
                     cull_kernel<false><<<rgrid, 256, 0, ctx->stream>>>(p);
                 const uint32_t cgrid = (uint32_t)(ctx->sm_count * ctx->occ_coarse);
                 if (voxel)
-                    coarse_kernel<8, true><<<cgrid, 256, 0, ctx->stream>>>(p);
+                    coarse_kernel<kCoarseMinBlocks, true><<<cgrid, 256, 0, ctx->stream>>>(p);
                 else  // (8 blocks/SM at 32 registers with 28 B spilled measured 1-3 % faster than 6 blocks at 38 without)
-                    coarse_kernel<8, false><<<cgrid, 256, 0, ctx->stream>>>(p);
+                    coarse_kernel<kCoarseMinBlocks, false><<<cgrid, 256, 0, ctx->stream>>>(p);
             }
             Span s(ctx, K_MARCH, 1);
             const size_t pad_bytes = (size_t)p.map.pad_words * 4;
