@@ -1186,7 +1186,7 @@ int prv_set_camera(prv_ctx* ctx, const prv_intrinsics* intr, double max_range) {
             PRV_GUARD_END(ctx, "prv_set_camera")
         } else {
             const char* e = getenv("PRV_DEPROJ_TABLE");  // A/B switch: 0 = the march evaluates deproject_pixel per ray
-            if (!(e && e[0] == '0')) {
+            if (!(e && e[0] == '0') && ((size_t)intr->width + 1) * ((size_t)intr->height + 1) * 8 <= ((size_t)1 << 30)) {  // (an image too large for a 1 GiB table: per ray)
                 CU(cudaSetDevice(ctx->device));
                 CU(join_score(ctx));
                 const size_t GW = (size_t)intr->width + 1, GH = (size_t)intr->height + 1;
